@@ -1,0 +1,67 @@
+"""Generates tests/golden/{bunny.npz,golden.json,tables_small.npz} from the REFERENCE ITSELF.
+
+Run in the build container (needs /root/reference):   python tests/golden/make_golden.py
+
+Every number written here is an output of the reference's unmodified src/cpu_voxelizer.cpp,
+compiled by oracle/Makefile into oracle/_ref/libvoxref.so and driven through oracle/ref_driver.cpp
+(bbox -> createMeshBBCube -> voxinfo -> cpu_voxelize_mesh{,_solid}), with OMP_NUM_THREADS=1 (the
+result is thread-count independent — OR/XOR commute — and one thread is the fast setting).
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import oracle  # noqa: E402
+from cuda_voxelizer_b200 import meshio  # noqa: E402
+
+REF_BUNNY = "/root/reference/test_models/bunny.OBJ"
+
+
+def main():
+    only_missing = "--update" in sys.argv
+    verts, faces = meshio.read_obj(REF_BUNNY)
+    assert verts.shape == (2557, 3) and faces.shape == (5110, 3)
+    np.savez_compressed(os.path.join(HERE, "bunny.npz"), verts=verts, faces=faces)
+
+    import cases
+    out_path = os.path.join(HERE, "golden.json")
+    golden = json.load(open(out_path)) if (only_missing and os.path.exists(out_path)) else {}
+    small_tables = {}
+    meshes = {}
+    for name, g, solid, morton in cases.GOLDEN_CASES:
+        key = cases.case_key(name, g, solid, morton)
+        if key in golden and only_missing:
+            continue
+        if name not in meshes:
+            meshes.clear()
+            meshes[name] = cases.mesh(name)
+        v, f = meshes[name]
+        t0 = time.time()
+        table, ms = oracle.ref_voxelize(v, f, g, solid=solid, morton=morton, threads=1, return_ms=True)
+        mn, mx, unit = oracle.ref_voxinfo(v, g, len(f))
+        golden[key] = {
+            "n_verts": int(len(v)), "n_tris": int(len(f)),
+            "popcount": oracle.popcount(table), "fnv1a64": "%016x" % oracle.fnv1a64(table),
+            "bbox_min": [float(x) for x in mn], "bbox_max": [float(x) for x in mx], "unit": [float(x) for x in unit],
+            "ref_ms_1thread": round(ms, 2),
+        }
+        if g <= 64:
+            small_tables[key] = table
+        print("%-55s popcount %12d  %s  ref %.1f ms (total %.1fs)" % (key, golden[key]["popcount"], golden[key]["fnv1a64"], ms, time.time() - t0), flush=True)
+        del table
+        json.dump(golden, open(out_path, "w"), indent=1, sort_keys=True)
+    if small_tables:
+        np.savez_compressed(os.path.join(HERE, "tables_small.npz"), **small_tables)
+    print("voxinfo layout:", oracle.ref_voxinfo_layout())
+
+
+if __name__ == "__main__":
+    main()
