@@ -1,0 +1,11 @@
+"""cuda_voxelizer_b200 — B200-native (sm_100a) voxelization hot path behind the reference's API.
+
+The product is the shared library ``libvoxb200.so`` (C ABI: include/voxb200.h; C++ drop-in symbols:
+include/voxelize_dropin.h) and the ``bin/cuda_voxelizer`` CLI.  This package is the thin Python host
+mirror used by the tests and the benchmark.
+"""
+from . import meshgen, meshio  # noqa: F401
+from ._lib import ACCUMULATE, MORTON, SOLID, TRIS_SOA4, Grid, Region, VoxError  # noqa: F401
+from .api import (device_count, download, grid_from_verts, init, last_counters, launch_count, make_grid,  # noqa: F401
+                  morton_encode, partition, table_bytes, upload_indexed, upload_soup, voxelize, voxelize_host,
+                  voxelize_solid)

@@ -1,0 +1,166 @@
+"""Host-side mirror of the reference's voxelization interface, over the C ABI.
+
+Names follow the reference: ``voxelize`` / ``voxelize_solid`` (main.cpp:23-24), ``voxinfo``
+(util.h:50-69) -> :class:`Grid`, ``meshToGPU_managed`` (main.cpp:61-80) -> :func:`upload_soup` /
+:func:`upload_indexed`.  PyTorch is used only as the owner of device memory and streams.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import ACCUMULATE, MORTON, SOLID, TRIS_SOA4, Grid, Region, VoxError, check  # noqa: F401
+
+
+def _f3(a):
+    return (C.c_float * 3)(*[float(x) for x in a])
+
+
+def device_count():
+    n = C.c_int(0)
+    check(_lib.lib().voxb200_device_count(C.byref(n)))
+    return n.value
+
+
+def init(device=0):
+    check(_lib.lib().voxb200_init(int(device)))
+
+
+def table_bytes(gridsize):
+    return int(_lib.lib().voxb200_table_bytes(int(gridsize)))
+
+
+def morton_encode(x, y, z):
+    return int(_lib.lib().voxb200_morton_encode(int(x), int(y), int(z)))
+
+
+def make_grid(mesh_min, mesh_max, gridsize, n_triangles):
+    """createMeshBBCube + voxinfo ctor (util.h:56-61,80-110) on the host, bit-identical."""
+    g = Grid()
+    check(_lib.lib().voxb200_make_grid(_f3(mesh_min), _f3(mesh_max), int(gridsize), int(n_triangles), C.byref(g)))
+    return g
+
+
+def grid_from_verts(verts, gridsize, n_triangles):
+    verts = np.asarray(verts, np.float32).reshape(-1, 3)
+    return make_grid(verts.min(axis=0), verts.max(axis=0), gridsize, n_triangles)
+
+
+def partition(gridsize, morton, part, n_parts):
+    """Region of rank ``part``: z-slab (linear) or aligned morton block; returns (Region, bytes)."""
+    r = Region()
+    nbytes = C.c_size_t(0)
+    check(_lib.lib().voxb200_partition(int(gridsize), int(bool(morton)), int(part), int(n_parts), C.byref(r), C.byref(nbytes)))
+    return r, nbytes.value
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+
+def _run(fn, grid, tris, table, flags, region, stream):
+    rp = C.byref(region) if region is not None else None
+    check(fn(C.byref(grid), C.c_void_p(tris.data_ptr()), C.c_void_p(table.data_ptr()), int(flags), rp, _stream_ptr(stream)))
+    return table
+
+
+def _new_table(grid, region, morton, device):
+    import torch
+    if region is None:
+        nbytes = table_bytes(grid.gridsize[0])
+    else:
+        sx, sy, sz = (region.hi[k] - region.lo[k] for k in range(3))
+        nbytes = (sx * sy * sz + 31) // 32 * 4
+    return torch.empty(nbytes // 4, dtype=torch.int32, device=device)
+
+
+def voxelize(grid, tris, table=None, morton=False, region=None, stream=None, accumulate=False, soa4=False):
+    """Surface voxelization (reference: voxelize(), voxelize.cu:192).  ``tris``: CUDA float32 tensor,
+    9 floats per triangle (or 3 float4 planes with ``soa4``).  Returns the uint32 bit table as an
+    int32 CUDA tensor (the region's words only when ``region`` is given).  Asynchronous on ``stream``."""
+    if table is None:
+        table = _new_table(grid, region, morton, tris.device)
+    flags = (MORTON if morton else 0) | (ACCUMULATE if accumulate else 0) | (TRIS_SOA4 if soa4 else 0)
+    return _run(_lib.lib().voxb200_surface, grid, tris, table, flags, region, stream)
+
+
+def voxelize_solid(grid, tris, table=None, morton=False, region=None, stream=None, accumulate=False, soa4=False):
+    """Solid voxelization (reference: voxelize_solid(), voxelize_solid.cu:147)."""
+    if table is None:
+        table = _new_table(grid, region, morton, tris.device)
+    flags = (MORTON if morton else 0) | (ACCUMULATE if accumulate else 0) | (TRIS_SOA4 if soa4 else 0)
+    return _run(_lib.lib().voxb200_solid, grid, tris, table, flags, region, stream)
+
+
+def voxelize_host(grid, host_tris, host_table=None, solid=False, morton=False, region=None):
+    """End to end with host buffers (numpy or pinned torch CPU tensors): H2D + voxelize + D2H.
+    Returns (table, timing_ms[h2d, voxelize, d2h, total])."""
+    def ptr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+    if host_table is None:
+        if region is None:
+            nbytes = table_bytes(grid.gridsize[0])
+        else:
+            sx, sy, sz = (region.hi[k] - region.lo[k] for k in range(3))
+            nbytes = (sx * sy * sz + 31) // 32 * 4
+        host_table = np.empty(nbytes // 4, np.uint32)
+    timing = (C.c_float * 4)()
+    flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+    rp = C.byref(region) if region is not None else None
+    check(_lib.lib().voxb200_voxelize_host(C.byref(grid), C.c_void_p(ptr(host_tris)), C.c_void_p(ptr(host_table)), flags, rp, timing))
+    return host_table, [float(t) for t in timing]
+
+
+class DeviceBuffer:
+    """A device allocation made by the library (voxb200_upload_*); freed on close()/GC."""
+
+    def __init__(self, ptr, nbytes):
+        self.ptr, self.nbytes = ptr, nbytes
+
+    def data_ptr(self):
+        return self.ptr
+
+    def close(self):
+        if self.ptr:
+            _lib.lib().voxb200_free(C.c_void_p(self.ptr))
+            self.ptr = 0
+
+    __del__ = close
+
+
+def upload_soup(host_tris, soa4=False, stream=0):
+    """Triangle soup upload (reference: meshToGPU_managed, main.cpp:61-80)."""
+    a = np.ascontiguousarray(host_tris, np.float32).reshape(-1, 9)
+    out = C.c_void_p(0)
+    check(_lib.lib().voxb200_upload_soup(C.c_void_p(a.ctypes.data), len(a), int(soa4), C.byref(out), C.c_void_p(stream)))
+    return DeviceBuffer(out.value, len(a) * (48 if soa4 else 36))
+
+
+def upload_indexed(verts, faces, soa4=False, want_bbox=True, stream=0):
+    """Indexed mesh upload with device-side expansion and bbox reduction.  Returns (buffer, min, max)."""
+    v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3)
+    f = np.ascontiguousarray(faces, np.int32).reshape(-1, 3)
+    out = C.c_void_p(0)
+    mn, mx = (C.c_float * 3)(), (C.c_float * 3)()
+    check(_lib.lib().voxb200_upload_indexed(C.c_void_p(v.ctypes.data), len(v), C.c_void_p(f.ctypes.data), len(f), int(soa4),
+                                            C.byref(out), mn if want_bbox else None, mx if want_bbox else None, C.c_void_p(stream)))
+    return DeviceBuffer(out.value, len(f) * (48 if soa4 else 36)), np.array(mn[:], np.float32), np.array(mx[:], np.float32)
+
+
+def download(buf_ptr, nbytes, stream=0):
+    out = np.empty(nbytes // 4, np.uint32)
+    check(_lib.lib().voxb200_memcpy_d2h(C.c_void_p(out.ctypes.data), C.c_void_p(buf_ptr), nbytes, C.c_void_p(stream)))
+    return out
+
+
+def launch_count(reset=False):
+    return int(_lib.lib().voxb200_launch_count(int(reset)))
+
+
+def last_counters():
+    out = (C.c_uint64 * 4)()
+    check(_lib.lib().voxb200_last_counters(out))
+    return {"coop_triangles": int(out[0]), "coop_items": int(out[1]), "solid_clamped": int(out[2])}

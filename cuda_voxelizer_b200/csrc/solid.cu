@@ -1,0 +1,225 @@
+// solid.cu — solid voxelization for sm_100a (replaces voxelize_solid.cu:73-193 of the reference).
+//
+// The reference flips every voxel x in [0, xmax] of each accepted (y,z) column with one atomicXor
+// per voxel (voxelize_solid.cu:124-137; cpu_voxelizer.cpp:297-308).  XOR is associative and
+// commutative, so the same table results from
+//   (1) MARK:  one atomicXor of the single bit (xmax, y, z) per accepted column sample, then
+//   (2) SCAN:  a suffix-XOR along x of every (y,z) row: out(x) = XOR of marks at x' >= x,
+// which turns O(G) atomics per column hit into one, and makes the fill a coalesced streaming pass.
+// With the MSB-first word layout a suffix over x is a prefix over bit positions inside a word
+// (w ^= w<<1; w ^= w<<2; … w<<16) plus a carry = parity of all later words of the row.
+//
+// Schedule: zero_kernel -> solid_tri_kernel (thread per triangle; triangles with many samples are
+// queued) -> solid_coop_kernel (warp per block of samples of a queued triangle) -> solid_scan_kernel.
+// MARK+SCAN needs a linear table whose rows are whole words (G a power of two >= 32); every other
+// case (morton order, odd grid sizes) takes the DIRECT mode, which flips the run itself, one atomic
+// per touched word.
+#include "vox_internal.h"
+
+namespace voxb {
+
+constexpr int kBlock = 256;
+constexpr int kSmallSamples = 64;     // (y,z) samples a single thread finishes itself
+constexpr int kSamplesPerItem = 256;  // samples per cooperative work item (8 per lane)
+
+__device__ __forceinline__ bool clip_samples_to_region(const GridParams& g, SolidSetup& s) {
+	s.y0 = max(s.y0, g.ry0); s.y1 = min(s.y1, g.ry1 - 1);
+	s.z0 = max(s.z0, g.rz0); s.z1 = min(s.z1, g.rz1 - 1);
+	return !s.skip && s.y0 <= s.y1 && s.z0 <= s.z1;
+}
+
+// One centre sample (y,z) of one triangle: accept test, xmax, then mark or flip.
+template <bool SCAN, bool MORTON>
+__device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams& g, int y, int z,
+                                           unsigned int* __restrict__ table, unsigned long long* __restrict__ counters) {
+	const float py = solid_center(y, g.uy), pz = solid_center(z, g.uz);
+	if (!solid_sample(s, py, pz)) return;
+	int xmax = solid_xmax(s, g, py, pz);
+	// The reference leaves xmax unclamped: < 0 wraps to a 2^32-iteration out-of-bounds loop on the CPU,
+	// >= G writes out of bounds.  Skip / clamp instead and count the event.
+	if (xmax < 0) { atomicAdd(counters + kCtrSolidClamp, 1ull); return; }
+	if (xmax > g.G - 1) { atomicAdd(counters + kCtrSolidClamp, 1ull); xmax = g.G - 1; }
+	if (SCAN) {
+		const unsigned long long idx = voxel_index<false>(g, xmax, y, z);
+		atomicXor(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
+	} else {
+		WordRun<true> run;
+		const int xa = max(0, g.rx0), xb = min(xmax, g.rx1 - 1);
+		for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<MORTON>(g, x, y, z));
+		run.flush(table);
+	}
+}
+
+template <bool SCAN, bool MORTON, bool SOA4>
+__global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, const float* __restrict__ tris,
+                                                           unsigned int* __restrict__ table,
+                                                           unsigned long long* __restrict__ counters,
+                                                           uint2* __restrict__ queue) {
+	__shared__ __align__(16) float stage[SOA4 ? 4 : kBlock * 9];
+	const unsigned long long block_first = (unsigned long long)blockIdx.x * kBlock;
+	const unsigned long long i = block_first + threadIdx.x;
+	Tri t;
+	bool valid;
+	if (SOA4) {
+		valid = i < g.n_tris;
+		if (valid) load_tri_soa4(tris, g.n_tris, i, t);
+	} else {
+		load_tri_block_aos<kBlock>(tris, g.n_tris, block_first, stage, t, valid);
+	}
+	SolidSetup s;
+	bool live = false, big = false;
+	unsigned int items = 0u;
+	if (valid) {
+		shift_tri(t, g);
+		solid_setup(t, g, s);
+		live = clip_samples_to_region(g, s);
+		if (live) {
+			const long long samples = (long long)(s.y1 - s.y0 + 1) * (long long)(s.z1 - s.z0 + 1);
+			big = samples > kSmallSamples;
+			items = (unsigned int)((samples + kSamplesPerItem - 1) / kSamplesPerItem);
+		}
+	}
+	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
+	if (!live || big) return;
+	for (int y = s.y0; y <= s.y1; y++)
+		for (int z = s.z0; z <= s.z1; z++) solid_emit<SCAN, MORTON>(s, g, y, z, table, counters);
+}
+
+template <bool SCAN, bool MORTON, bool SOA4>
+__global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, const float* __restrict__ tris,
+                                                            unsigned int* __restrict__ table,
+                                                            unsigned long long* __restrict__ counters,
+                                                            const uint2* __restrict__ queue) {
+	const unsigned long long packed = counters[kCtrQueue];
+	const unsigned int n_entries = (unsigned int)(packed >> 32);
+	const unsigned int n_items = (unsigned int)packed;
+	const int lane = threadIdx.x & 31;
+	const unsigned int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+	const unsigned int n_warps = (gridDim.x * kBlock) >> 5;
+	for (unsigned int item = warp; item < n_items; item += n_warps) {
+		unsigned int lo = 0u, hi = n_entries - 1u;
+		while (lo < hi) {
+			const unsigned int mid = (lo + hi + 1u) >> 1;
+			if (__ldg(&queue[mid].y) <= item) lo = mid; else hi = mid - 1u;
+		}
+		const uint2 e = __ldg(&queue[lo]);
+		Tri t;
+		if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
+		shift_tri(t, g);
+		SolidSetup s;
+		solid_setup(t, g, s);
+		clip_samples_to_region(g, s);
+		const int nz = s.z1 - s.z0 + 1;
+		const long long samples = (long long)(s.y1 - s.y0 + 1) * (long long)nz;
+		const long long k0 = (long long)(item - e.y) * kSamplesPerItem;
+		const long long k1 = min(samples, k0 + (long long)kSamplesPerItem);
+		for (long long k = k0 + lane; k < k1; k += 32) {
+			const int y = s.y0 + (int)(k / nz), z = s.z0 + (int)(k % nz);
+			solid_emit<SCAN, MORTON>(s, g, y, z, table, counters);
+		}
+	}
+}
+
+// Suffix-XOR along x of every row.  One lane per word; rows are `seg` (= G/32, a power of two) words
+// long.  K = words per lane-column when a row is longer than a warp (seg = 32*K), processed from the
+// row's last 32-word chunk to its first with the parity carried across chunks.
+template <int K, bool XOR_INTO>
+__global__ void __launch_bounds__(kBlock) solid_scan_kernel(const unsigned int* __restrict__ marks,
+                                                            unsigned int* __restrict__ out, size_t n_words, int seg) {
+	const int lane = threadIdx.x & 31;
+	const size_t warp = ((size_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+	const size_t base = warp * (size_t)(32 * K);
+	if (base >= n_words) return;           // n_words is a multiple of 32*K when K > 1, of seg when K == 1
+	const int width = K > 1 ? 32 : seg;    // lanes per row segment
+	const int pos = lane & (width - 1);
+	unsigned int w[K];
+#pragma unroll
+	for (int c = 0; c < K; c++) {
+		const size_t at = base + (size_t)c * 32 + lane;
+		w[c] = at < n_words ? marks[at] : 0u;
+	}
+	unsigned int carry = 0u;               // parity of all later chunks of this row (uniform per segment)
+#pragma unroll
+	for (int c = K - 1; c >= 0; c--) {
+		unsigned int v = w[c];
+		v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
+		const unsigned int par = __popc(w[c]) & 1u;
+		unsigned int suf = par;            // inclusive suffix parity over lanes of the segment
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
+			if (d < width && pos + d < width) suf ^= dn;
+		}
+		const unsigned int later = (suf ^ par) ^ carry;      // words after mine in this row
+		if (later) v = ~v;
+		const size_t at = base + (size_t)c * 32 + lane;
+		if (at < n_words) out[at] = XOR_INTO ? (out[at] ^ v) : v;
+		if (K > 1) carry ^= __shfl_sync(0xffffffffu, suf, 0);   // whole-chunk parity
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool SCAN, bool MORTON, bool SOA4>
+static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_marks, cudaStream_t st) {
+	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
+	solid_tri_kernel<SCAN, MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.queue);
+	g_launch_count++;
+	cudaError_t err = cudaGetLastError();
+	if (err != cudaSuccess) return err;
+	int per_sm = 0;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<SCAN, MORTON, SOA4>, kBlock, 0);
+	if (err != cudaSuccess) return err;
+	if (per_sm < 1) per_sm = 1;
+	solid_coop_kernel<SCAN, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.queue);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+template <bool XOR_INTO>
+static cudaError_t run_scan(const unsigned int* marks, unsigned int* out, size_t n_words, int seg, cudaStream_t st) {
+	const int k = seg <= 32 ? 1 : seg / 32;
+	const size_t warps = (n_words + (size_t)32 * k - 1) / ((size_t)32 * k);
+	const unsigned int blocks = (unsigned int)((warps + (kBlock / 32) - 1) / (kBlock / 32));
+	switch (k) {
+		case 1: solid_scan_kernel<1, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
+		case 2: solid_scan_kernel<2, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
+		case 4: solid_scan_kernel<4, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
+		case 8: solid_scan_kernel<8, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
+		default: return cudaErrorInvalidValue;
+	}
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
+                         size_t region_words, const LaunchOpts& o, cudaStream_t st) {
+	cudaError_t err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	if (err != cudaSuccess) return err;
+	const bool pow2 = (g.G & (g.G - 1)) == 0;
+	const bool full_xy = g.rx0 == 0 && g.rx1 == g.G && g.ry0 == 0 && g.ry1 == g.G;
+	const bool scan = !o.morton && pow2 && g.G >= 32 && g.G <= 8192 && full_xy;
+	unsigned int* marks = d_table;
+	if (scan && o.accumulate) {
+		// marks must start from zero: stage them in library scratch and XOR the scanned rows into the table
+		err = ensure_scratch(ws, region_words);
+		if (err != cudaSuccess) return err;
+		marks = ws.scratch;
+	}
+	if (!o.accumulate || marks != d_table) {
+		err = launch_zero(ws, marks, region_words, st);
+		if (err != cudaSuccess) return err;
+	}
+	if (g.n_tris == 0) return cudaSuccess;
+	err = ensure_queue(ws, (size_t)g.n_tris);
+	if (err != cudaSuccess) return err;
+	if (scan) {
+		err = o.soa4 ? run_solid_marks<true, false, true>(ws, g, d_tris, marks, st) : run_solid_marks<true, false, false>(ws, g, d_tris, marks, st);
+		if (err != cudaSuccess) return err;
+		const int seg = g.G / 32;
+		return (marks != d_table) ? run_scan<true>(marks, d_table, region_words, seg, st) : run_scan<false>(marks, d_table, region_words, seg, st);
+	}
+	if (o.morton) return o.soa4 ? run_solid_marks<false, true, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, true, false>(ws, g, d_tris, d_table, st);
+	return o.soa4 ? run_solid_marks<false, false, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, false, false>(ws, g, d_tris, d_table, st);
+}
+
+}  // namespace voxb

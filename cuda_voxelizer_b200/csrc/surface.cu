@@ -1,0 +1,194 @@
+// surface.cu — surface voxelization for sm_100a (replaces voxelize.cu:58-238 of the reference).
+//
+// Schedule (one stream, no host synchronisation):
+//   zero_kernel            the region's table bytes, 16-byte stores           (skipped with ACCUMULATE)
+//   surface_tri_kernel     one thread per triangle: coalesced fetch, exact setup, grid bbox.  Triangles
+//                          with at most kSmallMax candidate voxels are finished by their thread (word-run
+//                          aggregated atomicOr); bigger ones are queued with a warp-aggregated reservation
+//                          of {queue slot, work-item range} through ONE packed 64-bit atomic per warp.
+//   surface_coop_kernel    persistent grid; each warp takes work items = (queued triangle, block of
+//                          kRowsPerItem (y,z) rows).  Rows failing the x-independent YZ edge tests are skipped
+//                          whole; the rest are swept 32 x at a time, lanes across x, so a table word is built
+//                          by one __ballot_sync and written by one atomicOr.
+//
+// Every voxel that is set passed the reference's exact per-voxel expression sequence (vox_exact.cuh).
+#include "vox_internal.h"
+
+namespace voxb {
+
+constexpr int kBlock = 256;
+constexpr int kSmallMax = 64;      // candidate voxels a single thread finishes itself
+constexpr int kRowsPerItem = 32;   // (y,z) rows per cooperative work item
+
+unsigned long long g_launch_count = 0;
+
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) zero_kernel(uint4* __restrict__ p, size_t n16) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+__global__ void __launch_bounds__(512) zero_words_kernel(unsigned int* __restrict__ p, size_t n) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0u;
+}
+
+cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st) {
+	if (words == 0) return cudaSuccess;
+	const int sms = ws.sm_count > 0 ? ws.sm_count : 148;
+	if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (words & 3u) == 0) {
+		const size_t n16 = words / 4;
+		size_t blocks = (n16 + 511) / 512;
+		if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
+		zero_kernel<<<(unsigned)blocks, 512, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+	} else {
+		size_t blocks = (words + 511) / 512;
+		if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
+		zero_words_kernel<<<(unsigned)blocks, 512, 0, st>>>(p, words);
+	}
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool clip_to_region(const GridParams& g, SurfSetup& s) {
+	s.x0 = max(s.x0, g.rx0); s.x1 = min(s.x1, g.rx1 - 1);
+	s.y0 = max(s.y0, g.ry0); s.y1 = min(s.y1, g.ry1 - 1);
+	s.z0 = max(s.z0, g.rz0); s.z1 = min(s.z1, g.rz1 - 1);
+	return s.x0 <= s.x1 && s.y0 <= s.y1 && s.z0 <= s.z1;
+}
+
+template <bool MORTON, bool SOA4>
+__global__ void __launch_bounds__(kBlock) surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
+                                                             unsigned int* __restrict__ table,
+                                                             unsigned long long* __restrict__ counters,
+                                                             uint2* __restrict__ queue) {
+	__shared__ __align__(16) float stage[SOA4 ? 4 : kBlock * 9];
+	const unsigned long long block_first = (unsigned long long)blockIdx.x * kBlock;
+	const unsigned long long i = block_first + threadIdx.x;
+	Tri t;
+	bool valid;
+	if (SOA4) {
+		valid = i < g.n_tris;
+		if (valid) load_tri_soa4(tris, g.n_tris, i, t);
+	} else {
+		load_tri_block_aos<kBlock>(tris, g.n_tris, block_first, stage, t, valid);
+	}
+	SurfSetup s;
+	bool live = false;
+	unsigned int items = 0u;
+	bool big = false;
+	if (valid) {
+		shift_tri(t, g);
+		surf_setup(t, g, s);
+		live = clip_to_region(g, s);
+		if (live) {
+			const long long rows = (long long)(s.y1 - s.y0 + 1) * (long long)(s.z1 - s.z0 + 1);
+			const long long cands = rows * (long long)(s.x1 - s.x0 + 1);
+			big = cands > kSmallMax;
+			items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
+		}
+	}
+	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
+	if (!live || big) return;
+
+	WordRun<false> run;
+	for (int z = s.z0; z <= s.z1; z++) {
+		for (int y = s.y0; y <= s.y1; y++) {
+			SurfRow row;
+			if (!surf_row(s, g, y, z, row)) continue;
+			for (int x = s.x0; x <= s.x1; x++)
+				if (surf_voxel(s, g, row, x)) run.add(table, g, voxel_index<MORTON>(g, x, y, z));
+		}
+	}
+	run.flush(table);
+}
+
+template <bool MORTON, bool SOA4>
+__global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g, const float* __restrict__ tris,
+                                                              unsigned int* __restrict__ table,
+                                                              const unsigned long long* __restrict__ counters,
+                                                              const uint2* __restrict__ queue) {
+	const unsigned long long packed = counters[kCtrQueue];
+	const unsigned int n_entries = (unsigned int)(packed >> 32);
+	const unsigned int n_items = (unsigned int)packed;
+	const int lane = threadIdx.x & 31;
+	const unsigned int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+	const unsigned int n_warps = (gridDim.x * kBlock) >> 5;
+	const bool aligned = (g.G & 31) == 0;
+
+	for (unsigned int item = warp; item < n_items; item += n_warps) {
+		unsigned int lo = 0u, hi = n_entries - 1u;
+		while (lo < hi) {
+			const unsigned int mid = (lo + hi + 1u) >> 1;
+			if (__ldg(&queue[mid].y) <= item) lo = mid; else hi = mid - 1u;
+		}
+		const uint2 e = __ldg(&queue[lo]);
+		Tri t;
+		if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
+		shift_tri(t, g);
+		SurfSetup s;
+		surf_setup(t, g, s);
+		clip_to_region(g, s);
+		const int ny = s.y1 - s.y0 + 1;
+		const long long rows = (long long)ny * (long long)(s.z1 - s.z0 + 1);
+		const long long r0 = (long long)(item - e.y) * kRowsPerItem;
+		const long long r1 = min(rows, r0 + (long long)kRowsPerItem);
+		for (long long r = r0; r < r1; r++) {
+			const int z = s.z0 + (int)(r / ny), y = s.y0 + (int)(r % ny);
+			SurfRow row;
+			if (!surf_row(s, g, y, z, row)) continue;
+			const unsigned long long row_idx = MORTON ? 0ull : (unsigned long long)g.G * ((unsigned long long)y + (unsigned long long)g.G * (unsigned long long)z);
+			for (int xb = s.x0 & ~31; xb <= s.x1; xb += 32) {
+				const int x = xb + lane;
+				const bool hit = (x >= s.x0) && (x <= s.x1) && surf_voxel(s, g, row, x);
+				if (MORTON) {
+					const unsigned long long idx = morton3((unsigned)x, (unsigned)y, (unsigned)z);
+					unsigned int m = hit ? (1u << (31u - (unsigned int)(idx & 31ull))) : 0u;
+					m |= __shfl_xor_sync(0xffffffffu, m, 1);     // 4 consecutive x share one morton word
+					m |= __shfl_xor_sync(0xffffffffu, m, 2);
+					if ((lane & 3) == 0 && m) atomicOr(table + ((idx >> 5) - g.word_base), m);
+				} else if (aligned) {
+					const unsigned int b = __ballot_sync(0xffffffffu, hit);
+					if (lane == 0 && b) atomicOr(table + (((row_idx + (unsigned long long)xb) >> 5) - g.word_base), __brev(b));
+				} else if (hit) {
+					const unsigned long long idx = row_idx + (unsigned long long)x;
+					atomicOr(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
+				}
+			}
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+template <bool MORTON, bool SOA4>
+static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table, cudaStream_t st) {
+	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
+	surface_tri_kernel<MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
+	g_launch_count++;
+	cudaError_t err = cudaGetLastError();
+	if (err != cudaSuccess) return err;
+	int per_sm = 0;
+	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
+	if (err != cudaSuccess) return err;
+	if (per_sm < 1) per_sm = 1;
+	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
+                           size_t region_words, const LaunchOpts& o, cudaStream_t st) {
+	cudaError_t err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	if (err != cudaSuccess) return err;
+	if (!o.accumulate) {
+		err = launch_zero(ws, d_table, region_words, st);
+		if (err != cudaSuccess) return err;
+	}
+	if (g.n_tris == 0) return cudaSuccess;
+	err = ensure_queue(ws, (size_t)g.n_tris);
+	if (err != cudaSuccess) return err;
+	if (o.morton) return o.soa4 ? run_surface<true, true>(ws, g, d_tris, d_table, st) : run_surface<true, false>(ws, g, d_tris, d_table, st);
+	return o.soa4 ? run_surface<false, true>(ws, g, d_tris, d_table, st) : run_surface<false, false>(ws, g, d_tris, d_table, st);
+}
+
+}  // namespace voxb

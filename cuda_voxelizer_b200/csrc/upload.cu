@@ -1,0 +1,110 @@
+// upload.cu — device side of the triangle upload path (replaces the serial host gather of
+// meshToGPU_managed, main.cpp:61-80): index expansion, AoS -> SoA float4 transposition and the
+// mesh bbox reduction (trimesh2 need_bbox, main.cpp:179) run on the GPU, so the PCIe transfer is
+// the indexed mesh (12 B/vertex + 12 B/face) instead of the 36 B/triangle soup.
+#include "vox_internal.h"
+
+namespace voxb {
+
+constexpr int kUpBlock = 256;
+
+__global__ void __launch_bounds__(kUpBlock) soup_to_soa4_kernel(const float* __restrict__ soup, float4* __restrict__ out, size_t n) {
+	const size_t i = (size_t)blockIdx.x * kUpBlock + threadIdx.x;
+	if (i >= n) return;
+	const float* p = soup + 9 * i;
+	out[i] = make_float4(__ldg(p + 0), __ldg(p + 1), __ldg(p + 2), 0.0f);
+	out[n + i] = make_float4(__ldg(p + 3), __ldg(p + 4), __ldg(p + 5), 0.0f);
+	out[2 * n + i] = make_float4(__ldg(p + 6), __ldg(p + 7), __ldg(p + 8), 0.0f);
+}
+
+template <bool SOA4>
+__global__ void __launch_bounds__(kUpBlock) expand_indexed_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
+                                                                  size_t n_faces, float* __restrict__ out) {
+	const size_t i = (size_t)blockIdx.x * kUpBlock + threadIdx.x;
+	if (i >= n_faces) return;
+	const int a = __ldg(faces + 3 * i), b = __ldg(faces + 3 * i + 1), c = __ldg(faces + 3 * i + 2);
+	const float* pa = verts + 3 * (size_t)a;
+	const float* pb = verts + 3 * (size_t)b;
+	const float* pc = verts + 3 * (size_t)c;
+	if (SOA4) {
+		float4* o = reinterpret_cast<float4*>(out);
+		o[i] = make_float4(__ldg(pa), __ldg(pa + 1), __ldg(pa + 2), 0.0f);
+		o[n_faces + i] = make_float4(__ldg(pb), __ldg(pb + 1), __ldg(pb + 2), 0.0f);
+		o[2 * n_faces + i] = make_float4(__ldg(pc), __ldg(pc + 1), __ldg(pc + 2), 0.0f);
+	} else {
+		float* o = out + 9 * i;
+		o[0] = __ldg(pa); o[1] = __ldg(pa + 1); o[2] = __ldg(pa + 2);
+		o[3] = __ldg(pb); o[4] = __ldg(pb + 1); o[5] = __ldg(pb + 2);
+		o[6] = __ldg(pc); o[7] = __ldg(pc + 1); o[8] = __ldg(pc + 2);
+	}
+}
+
+// order-preserving float <-> uint key, so min/max can use integer atomics
+__device__ __forceinline__ unsigned int fkey(float f) {
+	const unsigned int b = __float_as_uint(f);
+	return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float funkey(unsigned int k) {
+	return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+__global__ void bbox_init_kernel(unsigned int* keys) {
+	if (threadIdx.x < 3) keys[threadIdx.x] = 0xffffffffu;
+	else if (threadIdx.x < 6) keys[threadIdx.x] = 0u;
+}
+__global__ void __launch_bounds__(kUpBlock) bbox_reduce_kernel(const float* __restrict__ verts, size_t n_verts, unsigned int* keys) {
+	unsigned int lo[3] = {0xffffffffu, 0xffffffffu, 0xffffffffu}, hi[3] = {0u, 0u, 0u};
+	const size_t stride = (size_t)gridDim.x * kUpBlock;
+	for (size_t i = (size_t)blockIdx.x * kUpBlock + threadIdx.x; i < n_verts; i += stride) {
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const unsigned int key = fkey(__ldg(verts + 3 * i + k));
+			lo[k] = min(lo[k], key);
+			hi[k] = max(hi[k], key);
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < 3; k++) {
+		lo[k] = __reduce_min_sync(0xffffffffu, lo[k]);
+		hi[k] = __reduce_max_sync(0xffffffffu, hi[k]);
+	}
+	if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+		for (int k = 0; k < 3; k++) { atomicMin(keys + k, lo[k]); atomicMax(keys + 3 + k, hi[k]); }
+	}
+}
+__global__ void bbox_decode_kernel(unsigned int* keys) {
+	if (threadIdx.x < 6) {
+		const float f = funkey(keys[threadIdx.x]);
+		reinterpret_cast<float*>(keys)[threadIdx.x] = f;
+	}
+}
+
+cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tris, cudaStream_t st) {
+	if (n_tris == 0) return cudaSuccess;
+	soup_to_soa4_kernel<<<(unsigned)((n_tris + kUpBlock - 1) / kUpBlock), kUpBlock, 0, st>>>(d_soup, reinterpret_cast<float4*>(d_soa4), n_tris);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t, bool soa4, float* d_out, cudaStream_t st) {
+	if (n_faces == 0) return cudaSuccess;
+	const unsigned blocks = (unsigned)((n_faces + kUpBlock - 1) / kUpBlock);
+	if (soa4) expand_indexed_kernel<true><<<blocks, kUpBlock, 0, st>>>(d_verts, d_faces, n_faces, d_out);
+	else expand_indexed_kernel<false><<<blocks, kUpBlock, 0, st>>>(d_verts, d_faces, n_faces, d_out);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st) {
+	unsigned int* keys = reinterpret_cast<unsigned int*>(d_minmax6);
+	bbox_init_kernel<<<1, 32, 0, st>>>(keys);
+	size_t blocks = (n_verts + kUpBlock - 1) / kUpBlock;
+	if (blocks > 148 * 8) blocks = 148 * 8;
+	bbox_reduce_kernel<<<(unsigned)blocks, kUpBlock, 0, st>>>(d_verts, n_verts, keys);
+	bbox_decode_kernel<<<1, 32, 0, st>>>(keys);
+	g_launch_count += 3;
+	return cudaGetLastError();
+}
+
+}  // namespace voxb

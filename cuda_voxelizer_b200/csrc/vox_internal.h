@@ -1,0 +1,54 @@
+// vox_internal.h — launcher interface between the C ABI (vox_abi.cu) and the kernel TUs.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "vox_exact.cuh"
+
+namespace voxb {
+
+// Device scratch owned by the library, one per device, grown on demand (never shrunk).
+struct Workspace {
+	int device = -1;
+	int sm_count = 0;
+	unsigned long long* counters = nullptr;   // kNumCounters x u64, zeroed at the start of every call
+	uint2* queue = nullptr;                   // cooperative-path queue: {triangle, first work item}
+	size_t queue_cap = 0;                     // entries
+	unsigned int* scratch = nullptr;          // solid: mark table for ACCUMULATE / morton modes
+	size_t scratch_words = 0;
+};
+
+enum Counter {
+	kCtrQueue = 0,        // packed: (queue entries << 32) | work items
+	kCtrClaim = 1,        // next work item to hand out (dynamic scheduling)
+	kCtrSolidClamp = 2,   // solid samples whose xmax fell outside [0, G-1]
+	kNumCounters = 8
+};
+
+struct LaunchOpts {
+	bool morton;
+	bool accumulate;
+	bool soa4;
+};
+
+extern unsigned long long g_launch_count;   // kernels launched by this library (voxb200_launch_count)
+
+cudaError_t ensure_queue(Workspace& ws, size_t entries);
+cudaError_t ensure_scratch(Workspace& ws, size_t words);
+
+// Zeroes `words` 32-bit words at p (own kernel: 16-byte stores, grid sized to the SM count).
+cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st);
+
+// The surface path (voxelize.cu:58-238 replaced): [zero] + per-triangle kernel + cooperative kernel.
+cudaError_t launch_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
+                           size_t region_words, const LaunchOpts& o, cudaStream_t st);
+// The solid path (voxelize_solid.cu:73-193 replaced): [zero] + mark kernels + column suffix-XOR scan.
+cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
+                         size_t region_words, const LaunchOpts& o, cudaStream_t st);
+
+// Upload helpers (main.cpp:61-80 replaced)
+cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tris, cudaStream_t st);
+cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t n_verts,
+                                  bool soa4, float* d_out, cudaStream_t st);
+cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);
+
+}  // namespace voxb

@@ -1,0 +1,149 @@
+/*
+ * voxb200.h — C ABI of the B200-native voxelization hot path.
+ *
+ * This is the drop-in boundary for the hot path of Forceflow/cuda_voxelizer.
+ * Plain pointers and sizes only; every function returns 0 on success or a non-zero VOXB200_E*
+ * code, with a message retrievable through voxb200_last_error().  The reference reports CUDA
+ * failures by printing and exit(EXIT_FAILURE) (src/libs/cuda/helper_cuda.h:566-579); the C++
+ * drop-in symbols in voxelize_dropin.h reproduce that on top of these status codes.
+ *
+ * There is NO CPU fallback behind this ABI: without a CUDA device every compute entry point fails
+ * with VOXB200_ENODEVICE.
+ *
+ * Reference interfaces replaced (file:line into the reference tree):
+ *   voxb200_init / voxb200_device_count ... initCuda()                    src/util_cuda.cpp:4-42
+ *   voxb200_make_grid .................... createMeshBBCube + voxinfo     src/util.h:56-61, 80-110 (main.cpp:184-186)
+ *   voxb200_table_bytes .................. vtable_size                    src/main.cpp:190
+ *   voxb200_upload_soup / _indexed ....... meshToGPU_managed()            src/main.cpp:61-80
+ *   voxb200_surface ...................... voxelize()                     src/voxelize.cu:192-238 (kernel :58-190)
+ *   voxb200_solid ........................ voxelize_solid()               src/voxelize_solid.cu:147-193 (kernel :73-145)
+ *   voxb200_morton_encode ................ mortonEncode_LUT()             src/voxelize.cuh:20-34
+ *   voxb200_voxelize_host ................ main.cpp:203-222 (upload + voxelize + table read-back by the writers)
+ *   bit-table layout ..................... setBit / checkVoxel            src/voxelize.cu:50-55, src/util.h:25-38
+ */
+#ifndef VOXB200_H
+#define VOXB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ------------------------------------------------------------------------- */
+#define VOXB200_OK            0
+#define VOXB200_ENODEVICE     1   /* no CUDA device / device is not sm_100                          */
+#define VOXB200_ECUDA         2   /* a CUDA runtime call failed (see voxb200_last_error)            */
+#define VOXB200_EINVAL        3   /* bad argument (NULL pointer, empty region, unsupported grid)    */
+#define VOXB200_ENOMEM        4   /* device or pinned-host allocation failed                        */
+
+/* ---- flags for voxb200_surface / voxb200_solid / voxb200_voxelize_host --------------------- */
+#define VOXB200_MORTON        1u  /* morton-ordered table (reference: -o morton, morton_code=true)  */
+#define VOXB200_ACCUMULATE    2u  /* OR / XOR into the table's current content instead of clearing  */
+                                  /* it first — the reference's exact semantics (it never clears,   */
+                                  /* main.cpp:214)                                                  */
+#define VOXB200_TRIS_SOA4     4u  /* triangles are 3 planes of float4 (v0|v1|v2, .w ignored), each  */
+                                  /* plane n_triangles long — the layout voxb200_upload_* produce   */
+                                  /* with soa4=1.  Default: the reference's 9-float AoS records.    */
+#define VOXB200_SOLID         8u  /* voxb200_voxelize_host only: solid instead of surface           */
+
+/*
+ * Plain-C mirror of the reference's `voxinfo` (src/util.h:50-69): byte-identical 64-byte layout
+ * (bbox.min @0, bbox.max @12, gridsize @24, n_triangles @40, unit @48; alignment 8), so a
+ * `const voxinfo*` can be passed where a `const voxb200_grid*` is expected.
+ */
+typedef struct voxb200_grid {
+	float bbox_min[3];
+	float bbox_max[3];
+	unsigned int gridsize[3];
+	size_t n_triangles;
+	float unit[3];
+} voxb200_grid;
+
+/*
+ * The part of the grid one call (one GPU) owns.  lo inclusive, hi exclusive, in voxel coordinates.
+ * The table pointer passed alongside addresses ONLY this region: word 0 of it is the word holding
+ * the region's first voxel.  The region must be contiguous in the chosen ordering:
+ *   linear: full x and y range, any z range (a z-slab)          — G*G*(hi.z-lo.z)/8 bytes
+ *   morton: a power-of-two aligned box produced by voxb200_partition (z halves, zy quadrants, octants…)
+ * NULL means the whole grid.
+ */
+typedef struct voxb200_region {
+	int lo[3];
+	int hi[3];
+} voxb200_region;
+
+/* ---- device ------------------------------------------------------------------------------- */
+int voxb200_device_count(int* count);
+/* Selects `device` for the calling thread and checks it is a compute-capability-10.x part. */
+int voxb200_init(int device);
+const char* voxb200_last_error(void);
+
+/* ---- grid parameters (host arithmetic, bit-identical to the reference's) -------------------- */
+/* mesh_min/mesh_max: bbox over all mesh vertices.  Cube-ifies, pads by 1/10001, derives unit. */
+int voxb200_make_grid(const float mesh_min[3], const float mesh_max[3], unsigned int gridsize,
+                      size_t n_triangles, voxb200_grid* out);
+size_t voxb200_table_bytes(unsigned int gridsize);
+/* Region rank `part` of `n_parts` (n_parts a power of two <= 8 for morton; any n <= gridsize for
+ * linear).  Writes the region and its size in bytes. */
+int voxb200_partition(unsigned int gridsize, int morton, int part, int n_parts,
+                      voxb200_region* out, size_t* region_bytes);
+uint64_t voxb200_morton_encode(unsigned int x, unsigned int y, unsigned int z);
+
+/* ---- device memory ------------------------------------------------------------------------- */
+int voxb200_malloc(void** dptr, size_t bytes);
+int voxb200_free(void* dptr);
+int voxb200_memcpy_d2h(void* host, const void* dptr, size_t bytes, void* stream);
+
+/* ---- triangle upload ------------------------------------------------------------------------ */
+/*
+ * Host triangle soup (9 floats per triangle, model space) -> device.  soa4 = 0 keeps the
+ * reference's AoS records (36 B/tri); soa4 = 1 transposes on the device into 3 float4 planes
+ * (48 B/tri).  *d_tris is allocated here (voxb200_free it).  Asynchronous on `stream` apart from
+ * the staging copy into pinned memory.
+ */
+int voxb200_upload_soup(const float* host_tris9, size_t n_triangles, int soa4, float** d_tris, void* stream);
+/*
+ * Indexed mesh (what trimesh2 holds: 12 B/vertex + 12 B/face) -> device triangles, expanded on
+ * the GPU.  Also reduces the mesh bbox over all vertices on the device (trimesh2 need_bbox,
+ * main.cpp:179) when mesh_min/mesh_max are non-NULL (synchronises the stream in that case).
+ */
+int voxb200_upload_indexed(const float* host_verts, size_t n_verts, const int32_t* host_faces, size_t n_faces,
+                           int soa4, float** d_tris, float mesh_min[3], float mesh_max[3], void* stream);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/*
+ * d_tris and d_table are device-accessible pointers (cudaMalloc or cudaMallocManaged).  `stream`
+ * is a cudaStream_t (NULL = legacy default stream).  Work is enqueued on `stream`; the call does
+ * not synchronise.  Without VOXB200_ACCUMULATE the region's table bytes are zeroed first (that
+ * write is part of the timed path).  Results are bit-identical to the reference's CPU voxelizer
+ * (cpu_voxelizer.cpp) for the same voxinfo and triangles.
+ */
+int voxb200_surface(const voxb200_grid* grid, const float* d_tris, unsigned int* d_table,
+                    unsigned int flags, const voxb200_region* region, void* stream);
+int voxb200_solid(const voxb200_grid* grid, const float* d_tris, unsigned int* d_table,
+                  unsigned int flags, const voxb200_region* region, void* stream);
+
+/*
+ * End to end with HOST buffers: upload the soup, voxelize (surface, or solid with VOXB200_SOLID),
+ * copy the table back, synchronise.  host_table must hold voxb200_table_bytes(G) bytes (or the
+ * region's bytes when region != NULL).  Fills timing_ms[0..3] (when non-NULL) with device-side
+ * milliseconds: H2D, voxelization, D2H, total.
+ */
+int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, unsigned int* host_table,
+                          unsigned int flags, const voxb200_region* region, float timing_ms[4]);
+
+/* ---- introspection ---------------------------------------------------------------------------- */
+/* Kernels launched by this library since the last reset (the bench's "gpu_launches"). */
+uint64_t voxb200_launch_count(int reset);
+/* Counters of the last surface/solid call, valid after the stream has been synchronised:
+ * [0] triangles routed to the cooperative (large-triangle) path, [1] work items of that path,
+ * [2] solid: samples clamped because xmax fell outside [0, G-1] (reference UB territory). */
+int voxb200_last_counters(uint64_t out[4]);
+const char* voxb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VOXB200_H */

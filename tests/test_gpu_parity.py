@@ -1,0 +1,248 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against
+  (1) the golden vectors generated from the reference itself (tests/golden/golden.json),
+  (2) the oracle restatement on the same seeded inputs (full-table compare at small sizes),
+  (3) size-independent properties at BASELINE.json's full sizes.
+Bit-exact everywhere: this is integer/bit output; there is no tolerance."""
+import numpy as np
+import pytest
+
+import cases
+import oracle
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def vb():
+    import cuda_voxelizer_b200 as vb
+    vb.init(0)          # raises (no fallback) when the library or a B200 is missing
+    return vb
+
+
+_mesh_cache = {}
+
+
+def _device_mesh(name):
+    if name not in _mesh_cache:
+        _mesh_cache.clear()
+        v, f = cases.mesh(name)
+        soup = oracle.soup(v, f)           # the reference's own 9-float layout (main.cpp:61-80)
+        _mesh_cache[name] = (v, f, torch.from_numpy(soup).cuda())
+    return _mesh_cache[name]
+
+
+def _run(vb, name, g, solid, morton, **kw):
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    table = fn(grid, d_tris, morton=bool(morton), **kw)
+    torch.cuda.synchronize()
+    return table.cpu().numpy().view(np.uint32), grid
+
+
+@pytest.mark.parametrize("name,g,solid,morton", cases.GOLDEN_CASES, ids=[cases.case_key(*c) for c in cases.GOLDEN_CASES])
+def test_matches_reference_golden(vb, golden, name, g, solid, morton):
+    want = golden[cases.case_key(name, g, solid, morton)]
+    table, grid = _run(vb, name, g, solid, morton)
+    assert [float(x) for x in grid.unit] == want["unit"]
+    assert table.nbytes == vb.table_bytes(g)
+    assert oracle.popcount(table) == want["popcount"]
+    assert "%016x" % oracle.fnv1a64(table) == want["fnv1a64"]
+    assert vb.last_counters()["solid_clamped"] == 0
+
+
+ORACLE_CASES = [c for c in cases.GOLDEN_CASES if c[1] <= 256]
+
+
+@pytest.mark.parametrize("name,g,solid,morton", ORACLE_CASES, ids=[cases.case_key(*c) for c in ORACLE_CASES])
+def test_full_table_equals_oracle(vb, name, g, solid, morton):
+    table, grid = _run(vb, name, g, solid, morton)
+    v, f, _ = _device_mesh(name)
+    mn, mx, unit = oracle.voxinfo(v, g)
+    want = (oracle.solid if solid else oracle.surface)(oracle.soup(v, f), mn, unit, g, morton)
+    diff = np.nonzero(table ^ want)[0]
+    assert len(diff) == 0, "first differing words: %s" % diff[:8]
+
+
+@pytest.mark.parametrize("g", [8, 16, 24, 40, 100])
+@pytest.mark.parametrize("solid", [0, 1])
+def test_odd_and_tiny_grids(vb, g, solid):
+    """Grid sizes whose rows are not whole words (and non powers of two) take the generic paths."""
+    name = "icosphere:16:64"
+    table, grid = _run(vb, name, g, solid, 0)
+    v, f, _ = _device_mesh(name)
+    mn, mx, unit = oracle.voxinfo(v, g)
+    want = (oracle.solid if solid else oracle.surface)(oracle.soup(v, f), mn, unit, g, 0)
+    assert np.array_equal(table, want)
+
+
+@pytest.mark.parametrize("name,g,solid", [("bunny", 128, 0), ("bunny", 128, 1), ("icosphere:64:128", 256, 0), ("icosphere:64:128", 256, 1)])
+def test_soa4_layout_gives_same_table(vb, name, g, solid):
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    a = fn(grid, d_tris)
+    t = d_tris.view(-1, 3, 3)
+    planes = torch.zeros(3, t.shape[0], 4, device="cuda")
+    planes[:, :, :3] = t.permute(1, 0, 2)
+    b = fn(grid, planes.contiguous().view(-1), soa4=True)
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("solid", [0, 1])
+@pytest.mark.parametrize("morton", [0, 1])
+def test_accumulate_is_or_xor_into(vb, solid, morton):
+    """Reference semantics: voxelize() ORs / voxelize_solid() XORs into whatever the table holds."""
+    name, g = "bunny", 64
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    clean = fn(grid, d_tris, morton=bool(morton)).clone()
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    prior = torch.randint(-2 ** 31, 2 ** 31 - 1, clean.shape, dtype=torch.int32, device="cuda", generator=gen)
+    table = prior.clone()
+    fn(grid, d_tris, table=table, morton=bool(morton), accumulate=True)
+    want = (prior ^ clean) if solid else (prior | clean)
+    assert torch.equal(table, want)
+
+
+@pytest.mark.parametrize("n_parts", [2, 4, 8])
+@pytest.mark.parametrize("solid,morton", [(0, 0), (1, 0), (0, 1), (1, 1)])
+def test_regions_concatenate_to_full_table(vb, n_parts, solid, morton):
+    """Multi-GPU contract: disjoint regions, no reduction — concatenation == 1-GPU table."""
+    name, g = "bunny", 128
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    full = fn(grid, d_tris, morton=bool(morton)).clone()
+    parts = []
+    for p in range(n_parts):
+        region, nbytes = vb.partition(g, morton, p, n_parts)
+        t = fn(grid, d_tris, morton=bool(morton), region=region)
+        assert t.numel() * 4 == nbytes
+        parts.append(t.clone())
+    assert torch.equal(torch.cat(parts), full)
+
+
+def test_uneven_z_slabs(vb):
+    name, g = "icosphere:16:64", 128
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    for fn in (vb.voxelize, vb.voxelize_solid):
+        full = fn(grid, d_tris).clone()
+        parts = []
+        for z0, z1 in ((0, 1), (1, 50), (50, 127), (127, 128)):
+            r = vb.Region()
+            r.lo[:] = [0, 0, z0]
+            r.hi[:] = [g, g, z1]
+            parts.append(fn(grid, d_tris, region=r).clone())
+        assert torch.equal(torch.cat(parts), full)
+
+
+def test_upload_paths(vb):
+    """Triangle upload (main.cpp:61-80 replaced): soup and indexed uploads, AoS and SoA4, plus the
+    device bbox reduction, all lead to the same table as torch-owned memory."""
+    name, g = "bunny", 128
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    want = vb.voxelize(grid, d_tris).clone()
+    soup = oracle.soup(v, f)
+    for soa4 in (False, True):
+        buf = vb.upload_soup(soup, soa4=soa4)
+        assert torch.equal(vb.voxelize(grid, buf, soa4=soa4, table=torch.empty_like(want)), want)
+        buf.close()
+        buf, mn, mx = vb.upload_indexed(v, f, soa4=soa4)
+        assert np.array_equal(mn, v.min(axis=0)) and np.array_equal(mx, v.max(axis=0))
+        assert torch.equal(vb.voxelize(grid, buf, soa4=soa4, table=torch.empty_like(want)), want)
+        buf.close()
+    with pytest.raises(vb.VoxError):
+        vb.upload_indexed(v, f + len(v))
+
+
+@pytest.mark.parametrize("solid,morton", [(0, 0), (1, 0), (0, 1)])
+def test_voxelize_host_end_to_end(vb, golden, solid, morton):
+    name, g = "bunny", 256
+    v, f, _ = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    soup = oracle.soup(v, f)
+    table, ms = vb.voxelize_host(grid, soup, solid=bool(solid), morton=bool(morton))
+    want = golden[cases.case_key(name, g, solid, morton)]
+    assert oracle.popcount(table) == want["popcount"] and "%016x" % oracle.fnv1a64(table) == want["fnv1a64"]
+    pinned = torch.from_numpy(soup).pin_memory()
+    out = torch.empty(vb.table_bytes(g) // 4, dtype=torch.int32).pin_memory()
+    vb.voxelize_host(grid, pinned, out, solid=bool(solid), morton=bool(morton))
+    assert np.array_equal(out.numpy().view(np.uint32), table)
+    assert len(ms) == 4 and ms[3] > 0
+
+
+def test_empty_and_degenerate_inputs(vb):
+    g = 64
+    grid = vb.make_grid([0, 0, 0], [1, 1, 1], g, 0)
+    t = vb.voxelize(grid, torch.zeros(9, device="cuda"))
+    assert int(t.abs().sum()) == 0
+    # zero-area and collinear triangles: NaN normal -> reference semantics restated by the oracle
+    soup = np.array([[0.2, 0.2, 0.2] * 3, [0.1, 0.1, 0.1, 0.5, 0.5, 0.5, 0.9, 0.9, 0.9], [0.3, 0.3, 0.3, 0.3, 0.3, 0.3, 0.7, 0.3, 0.3]], np.float32)
+    grid = vb.make_grid([0, 0, 0], [1, 1, 1], g, len(soup))
+    got = vb.voxelize(grid, torch.from_numpy(soup).cuda()).cpu().numpy().view(np.uint32)
+    want = oracle.surface(soup, np.array(grid.bbox_min[:], np.float32), np.array(grid.unit[:], np.float32), g)
+    assert np.array_equal(got, want)
+
+
+def test_invalid_arguments_report_einval(vb):
+    from cuda_voxelizer_b200 import _lib
+    grid = vb.make_grid([0, 0, 0], [1, 1, 1], 48, 1)
+    tris = torch.zeros(9, device="cuda")
+    with pytest.raises(vb.VoxError) as e:
+        vb.voxelize(grid, tris, morton=True)          # morton needs a power-of-two grid
+    assert e.value.code == _lib.EINVAL
+    grid.gridsize[1] = 32
+    with pytest.raises(vb.VoxError):
+        vb.voxelize(grid, tris)                       # non-cubic
+
+
+# ------------------------------------------------------------------ full-size properties
+def test_full_size_properties_config4(vb, golden):
+    """10M-triangle icosphere at 2048^3 (config 4): golden hash (checked above) plus properties that need
+    no oracle: z-slab sharding reproduces the table, every set voxel lies in the sphere's shell, and
+    re-voxelizing in accumulate mode is idempotent."""
+    name, g = "icosphere:708:1024", 2048
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    full = vb.voxelize(grid, d_tris)
+    again = full.clone()
+    vb.voxelize(grid, d_tris, table=again, accumulate=True)
+    assert torch.equal(again, full)
+    parts = []
+    for p in range(8):
+        region, _ = vb.partition(g, False, p, 8)
+        parts.append(vb.voxelize(grid, d_tris, region=region))
+    assert torch.equal(torch.cat(parts), full)
+    del parts, again
+    # shell property on one z-slice through the centre: set voxels are within ~2 voxels of radius 1024
+    words = g * g // 32
+    sl = full[1024 * words: 1025 * words].cpu().numpy().view(np.uint32)
+    bits = np.unpackbits(sl.view(np.uint8).reshape(-1, 4)[:, ::-1].reshape(-1)).reshape(g, g)
+    ys, xs = np.nonzero(bits)
+    unit = np.float64(grid.unit[0])
+    cx = (xs + 0.5) * unit + grid.bbox_min[0]
+    cy = (ys + 0.5) * unit + grid.bbox_min[1]
+    cz = (1024 + 0.5) * unit + grid.bbox_min[2]
+    r = np.sqrt(cx ** 2 + cy ** 2 + cz ** 2)
+    assert len(xs) > 5000 and np.all(np.abs(r - 1024.0) < 2.5)
+
+
+def test_full_size_solid_is_scan_of_surface_columns_config3(vb):
+    """Config 3 (1M-triangle icosphere, solid, 1024^3): popcount/hash are checked against the reference
+    golden above; here: the solid table equals the XOR of its z-slab shards, and the filled volume is
+    the sphere's to 0.01 %."""
+    name, g = "icosphere:224:512", 1024
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    full = vb.voxelize_solid(grid, d_tris)
+    parts = [vb.voxelize_solid(grid, d_tris, region=vb.partition(g, False, p, 4)[0]) for p in range(4)]
+    assert torch.equal(torch.cat(parts), full)
+    pop = oracle.popcount(full.cpu().numpy().view(np.uint32))
+    ideal = 4.0 / 3.0 * np.pi * 512.0 ** 3 / float(grid.unit[0]) ** 3
+    assert abs(pop - ideal) / ideal < 1e-4
