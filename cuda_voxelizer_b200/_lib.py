@@ -19,7 +19,7 @@ EXPORTS = [
     "voxb200_device_count", "voxb200_init", "voxb200_last_error", "voxb200_make_grid", "voxb200_table_bytes",
     "voxb200_partition", "voxb200_morton_encode", "voxb200_malloc", "voxb200_free", "voxb200_memcpy_d2h",
     "voxb200_upload_soup", "voxb200_upload_indexed", "voxb200_surface", "voxb200_solid", "voxb200_voxelize_host",
-    "voxb200_launch_count", "voxb200_last_counters", "voxb200_version",
+    "voxb200_launch_count", "voxb200_last_counters", "voxb200_version", "voxb200_set_profiling", "voxb200_phase_ms",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
     L.voxb200_launch_count.argtypes = [C.c_int]
     L.voxb200_launch_count.restype = C.c_uint64
     L.voxb200_last_counters.argtypes = [C.POINTER(C.c_uint64)]
+    L.voxb200_set_profiling.argtypes = [C.c_int]
+    L.voxb200_phase_ms.argtypes = [C.c_uint, f3]
     _lib = L
     return L
 

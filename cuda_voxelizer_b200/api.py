@@ -164,3 +164,14 @@ def last_counters():
     out = (C.c_uint64 * 4)()
     check(_lib.lib().voxb200_last_counters(out))
     return {"coop_triangles": int(out[0]), "coop_items": int(out[1]), "solid_clamped": int(out[2])}
+
+
+def set_profiling(on):
+    check(_lib.lib().voxb200_set_profiling(int(bool(on))))
+
+
+def phase_ms(call_index):
+    """[zero-fill, per-triangle kernel, cooperative kernel, solid scan] ms of the i-th profiled call."""
+    out = (C.c_float * 4)()
+    check(_lib.lib().voxb200_phase_ms(int(call_index), out))
+    return [float(x) for x in out]

@@ -164,10 +164,11 @@ static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const flo
 	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
 	solid_tri_kernel<SCAN, MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.queue);
 	g_launch_count++;
+	prof_mark(ws, 2, st);
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
-	int per_sm = 0;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<SCAN, MORTON, SOA4>, kBlock, 0);
+	static int per_sm = 0;
+	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<SCAN, MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
 	solid_coop_kernel<SCAN, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.queue);
@@ -193,7 +194,7 @@ static cudaError_t run_scan(const unsigned int* marks, unsigned int* out, size_t
 
 cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
                          size_t region_words, const LaunchOpts& o, cudaStream_t st) {
-	cudaError_t err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	cudaError_t err = ensure_queue(ws, (size_t)g.n_tris);
 	if (err != cudaSuccess) return err;
 	const bool pow2 = (g.G & (g.G - 1)) == 0;
 	const bool full_xy = g.rx0 == 0 && g.rx1 == g.G && g.ry0 == 0 && g.ry1 == g.G;
@@ -205,21 +206,31 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris
 		if (err != cudaSuccess) return err;
 		marks = ws.scratch;
 	}
+	err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	if (err != cudaSuccess) return err;
+	prof_mark(ws, 0, st);
 	if (!o.accumulate || marks != d_table) {
 		err = launch_zero(ws, marks, region_words, st);
 		if (err != cudaSuccess) return err;
 	}
-	if (g.n_tris == 0) return cudaSuccess;
-	err = ensure_queue(ws, (size_t)g.n_tris);
-	if (err != cudaSuccess) return err;
-	if (scan) {
-		err = o.soa4 ? run_solid_marks<true, false, true>(ws, g, d_tris, marks, st) : run_solid_marks<true, false, false>(ws, g, d_tris, marks, st);
+	prof_mark(ws, 1, st);
+	if (g.n_tris != 0) {
+		if (scan) err = o.soa4 ? run_solid_marks<true, false, true>(ws, g, d_tris, marks, st) : run_solid_marks<true, false, false>(ws, g, d_tris, marks, st);
+		else if (o.morton) err = o.soa4 ? run_solid_marks<false, true, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, true, false>(ws, g, d_tris, d_table, st);
+		else err = o.soa4 ? run_solid_marks<false, false, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, false, false>(ws, g, d_tris, d_table, st);
 		if (err != cudaSuccess) return err;
-		const int seg = g.G / 32;
-		return (marks != d_table) ? run_scan<true>(marks, d_table, region_words, seg, st) : run_scan<false>(marks, d_table, region_words, seg, st);
+	} else {
+		prof_mark(ws, 2, st);
 	}
-	if (o.morton) return o.soa4 ? run_solid_marks<false, true, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, true, false>(ws, g, d_tris, d_table, st);
-	return o.soa4 ? run_solid_marks<false, false, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, false, false>(ws, g, d_tris, d_table, st);
+	prof_mark(ws, 3, st);
+	if (scan && (g.n_tris != 0 || marks != d_table)) {
+		const int seg = g.G / 32;
+		err = (marks != d_table) ? run_scan<true>(marks, d_table, region_words, seg, st) : run_scan<false>(marks, d_table, region_words, seg, st);
+		if (err != cudaSuccess) return err;
+	}
+	prof_mark(ws, 4, st);
+	if (ws.prof_on) ws.prof_calls++;
+	return cudaSuccess;
 }
 
 }  // namespace voxb

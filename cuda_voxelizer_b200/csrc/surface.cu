@@ -57,6 +57,136 @@ __device__ __forceinline__ bool clip_to_region(const GridParams& g, SurfSetup& s
 	return s.x0 <= s.x1 && s.y0 <= s.y1 && s.z0 <= s.z1;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Micro path: a triangle whose (region-clipped) grid bbox is at most 3x3x3 voxels — every triangle of
+// a mesh tessellated near the voxel size.  All 27 candidates are evaluated in straight-line code with
+// no data-dependent branch, so the 32 triangles of a warp stay converged:
+//   * each test value is the reference's exact expression (same products, same left-to-right adds);
+//     the 2D edge functions are evaluated once per (x,y) / (y,z) / (z,x) cell instead of once per voxel;
+//   * a test's outcome is the SIGN BIT of its value, shifted into a reject mask with one funnel shift:
+//       edge test  "v < 0"          -> sign(min(v_e0, v_e1, v_e2))   (v is never -0: its last addend d_e never is)
+//       plane test "(s+d1)(s+d2) > 0" -> sign(0 - P)                 (0 - P is -0 for no P; NaN is canonical, sign clear)
+//   * voxel b = i + 3j + 9k survives iff it is inside the bbox and none of the four masks rejects it.
+// Survivors are written one (y,z) row at a time: the 3 x-bits of a row go out as one or two atomicOr.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {       // mask = (mask << 1) | signbit(v)
+	return __funnelshift_l(__float_as_uint(v), mask, 1);
+}
+
+template <bool MORTON>
+__device__ __forceinline__ void surf_micro3(const SurfSetup& s, const GridParams& g, unsigned int* __restrict__ table) {
+	float px[3], py[3], pz[3];
+#pragma unroll
+	for (int i = 0; i < 3; i++) {
+		px[i] = fmul((float)(s.x0 + i), g.ux);
+		py[i] = fmul((float)(s.y0 + i), g.uy);
+		pz[i] = fmul((float)(s.z0 + i), g.uz);
+	}
+	// plane: ((n.x*p.x + n.y*p.y) + n.z*p.z), then (s + d1) * (s + d2) > 0 rejects
+	float nxp[3], nyp[3], nzp[3];
+#pragma unroll
+	for (int i = 0; i < 3; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
+	unsigned int rej = 0u;
+#pragma unroll
+	for (int k = 2; k >= 0; k--)
+#pragma unroll
+		for (int j = 2; j >= 0; j--)
+#pragma unroll
+			for (int i = 2; i >= 0; i--) {
+				const float sdp = fadd(fadd(nxp[i], nyp[j]), nzp[k]);
+				const float prod = fmul(fadd(sdp, s.d1), fadd(sdp, s.d2));
+				rej = sign_in(rej, fsub(0.0f, prod));
+			}
+	// XY cells (i,j): bit i + 3j, replicated over k
+	unsigned int rxy = 0u, ryz = 0u, rzx = 0u;
+	{
+		float a[3][3], b[3][3];
+#pragma unroll
+		for (int e = 0; e < 3; e++)
+#pragma unroll
+			for (int i = 0; i < 3; i++) { a[e][i] = fmul(s.xy_a[e], px[i]); b[e][i] = fmul(s.xy_b[e], py[i]); }
+#pragma unroll
+		for (int j = 2; j >= 0; j--)
+#pragma unroll
+			for (int i = 2; i >= 0; i--) {
+				const float v0 = fadd(fadd(a[0][i], b[0][j]), s.xy_d[0]);
+				const float v1 = fadd(fadd(a[1][i], b[1][j]), s.xy_d[1]);
+				const float v2 = fadd(fadd(a[2][i], b[2][j]), s.xy_d[2]);
+				rxy = sign_in(rxy, fminf(fminf(v0, v1), v2));
+			}
+	}
+	// YZ cells (j,k): value = (n.x*p.y + n.y*p.z) + d; bit j + 3k, replicated over i
+	{
+		float a[3][3], b[3][3];
+#pragma unroll
+		for (int e = 0; e < 3; e++)
+#pragma unroll
+			for (int i = 0; i < 3; i++) { a[e][i] = fmul(s.yz_a[e], py[i]); b[e][i] = fmul(s.yz_b[e], pz[i]); }
+#pragma unroll
+		for (int k = 2; k >= 0; k--)
+#pragma unroll
+			for (int j = 2; j >= 0; j--) {
+				const float v0 = fadd(fadd(a[0][j], b[0][k]), s.yz_d[0]);
+				const float v1 = fadd(fadd(a[1][j], b[1][k]), s.yz_d[1]);
+				const float v2 = fadd(fadd(a[2][j], b[2][k]), s.yz_d[2]);
+				ryz = sign_in(ryz, fminf(fminf(v0, v1), v2));
+			}
+	}
+	// ZX cells (k,i): value = (n.x*p.z + n.y*p.x) + d; bit i + 3k, replicated over j
+	{
+		float a[3][3], b[3][3];
+#pragma unroll
+		for (int e = 0; e < 3; e++)
+#pragma unroll
+			for (int i = 0; i < 3; i++) { a[e][i] = fmul(s.zx_a[e], pz[i]); b[e][i] = fmul(s.zx_b[e], px[i]); }
+#pragma unroll
+		for (int k = 2; k >= 0; k--)
+#pragma unroll
+			for (int i = 2; i >= 0; i--) {
+				const float v0 = fadd(fadd(a[0][k], b[0][i]), s.zx_d[0]);
+				const float v1 = fadd(fadd(a[1][k], b[1][i]), s.zx_d[1]);
+				const float v2 = fadd(fadd(a[2][k], b[2][i]), s.zx_d[2]);
+				rzx = sign_in(rzx, fminf(fminf(v0, v1), v2));
+			}
+	}
+	// expand the 9-bit cell masks to the 27-bit voxel layout b = i + 3j + 9k
+	const unsigned int xy27 = rxy * 0x40201u;                                           // copies at +0, +9, +18
+	const unsigned int yz_s = (ryz & 0x1u) | ((ryz & 0x2u) << 2) | ((ryz & 0x4u) << 4) | ((ryz & 0x8u) << 6) | ((ryz & 0x10u) << 8) |
+	                          ((ryz & 0x20u) << 10) | ((ryz & 0x40u) << 12) | ((ryz & 0x80u) << 14) | ((ryz & 0x100u) << 16);   // bit (j+3k) -> 3j+9k
+	const unsigned int yz27 = yz_s * 7u;                                                // copies at +0, +1, +2
+	const unsigned int zx_s = (rzx & 0x7u) | ((rzx & 0x38u) << 6) | ((rzx & 0x1c0u) << 12);                                     // bit (i+3k) -> i+9k
+	const unsigned int zx27 = zx_s * 0x49u;                                             // copies at +0, +3, +6
+	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..2
+	const unsigned int valid = (((2u << ex) - 1u) * 0x1249249u) & (((8u << (3 * ey)) - 1u) * 0x40201u) & ((512u << (9 * ez)) - 1u);
+	unsigned int hit = valid & ~(rej | xy27 | yz27 | zx27);
+
+	if (MORTON) {
+		WordRun<false> run;
+		while (hit) {
+			const int b = __ffs(hit) - 1;
+			hit &= hit - 1u;
+			const int k = b / 9, j = (b - 9 * k) / 3, i = b - 9 * k - 3 * j;
+			run.add(table, g, morton3((unsigned)(s.x0 + i), (unsigned)(s.y0 + j), (unsigned)(s.z0 + k)));
+		}
+		run.flush(table);
+		return;
+	}
+	const unsigned long long G = (unsigned long long)g.G;
+	while (hit) {
+		const int r = (__ffs(hit) - 1) / 3;                    // row = j + 3k
+		const unsigned int bits = (hit >> (3 * r)) & 7u;        // x0, x0+1, x0+2
+		hit &= ~(7u << (3 * r));
+		const int k = r / 3, j = r - 3 * k;
+		const unsigned long long idx = (unsigned long long)s.x0 + G * ((unsigned long long)(s.y0 + j) + G * (unsigned long long)(s.z0 + k));
+		// voxel idx+t sits at bit 31-((idx+t)&31): put the row MSB-first into a 64-bit window over words w, w+1
+		const unsigned long long win = ((unsigned long long)(__brev(bits) >> 29) << 61) >> (unsigned int)(idx & 31ull);
+		const unsigned long long w = (idx >> 5) - g.word_base;
+		const unsigned int hi = (unsigned int)(win >> 32), lo = (unsigned int)win;
+		if (hi) atomicOr(table + w, hi);
+		if (lo) atomicOr(table + w + 1, lo);
+	}
+}
+
 template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
                                                              unsigned int* __restrict__ table,
@@ -90,6 +220,10 @@ __global__ void __launch_bounds__(kBlock) surface_tri_kernel(const GridParams g,
 	}
 	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
 	if (!live || big) return;
+	if (s.x1 - s.x0 <= 2 && s.y1 - s.y0 <= 2 && s.z1 - s.z0 <= 2) {
+		surf_micro3<MORTON>(s, g, table);
+		return;
+	}
 
 	WordRun<false> run;
 	for (int z = s.z0; z <= s.z1; z++) {
@@ -165,10 +299,11 @@ static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* 
 	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
 	surface_tri_kernel<MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
 	g_launch_count++;
+	prof_mark(ws, 2, st);
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
-	int per_sm = 0;
-	err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
+	static int per_sm = 0;
+	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
 	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
@@ -178,17 +313,27 @@ static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* 
 
 cudaError_t launch_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
                            size_t region_words, const LaunchOpts& o, cudaStream_t st) {
-	cudaError_t err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	cudaError_t err = ensure_queue(ws, (size_t)g.n_tris);
 	if (err != cudaSuccess) return err;
+	err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	if (err != cudaSuccess) return err;
+	prof_mark(ws, 0, st);
 	if (!o.accumulate) {
 		err = launch_zero(ws, d_table, region_words, st);
 		if (err != cudaSuccess) return err;
 	}
-	if (g.n_tris == 0) return cudaSuccess;
-	err = ensure_queue(ws, (size_t)g.n_tris);
-	if (err != cudaSuccess) return err;
-	if (o.morton) return o.soa4 ? run_surface<true, true>(ws, g, d_tris, d_table, st) : run_surface<true, false>(ws, g, d_tris, d_table, st);
-	return o.soa4 ? run_surface<false, true>(ws, g, d_tris, d_table, st) : run_surface<false, false>(ws, g, d_tris, d_table, st);
+	prof_mark(ws, 1, st);
+	if (g.n_tris != 0) {
+		if (o.morton) err = o.soa4 ? run_surface<true, true>(ws, g, d_tris, d_table, st) : run_surface<true, false>(ws, g, d_tris, d_table, st);
+		else err = o.soa4 ? run_surface<false, true>(ws, g, d_tris, d_table, st) : run_surface<false, false>(ws, g, d_tris, d_table, st);
+		if (err != cudaSuccess) return err;
+	} else {
+		prof_mark(ws, 2, st);
+	}
+	prof_mark(ws, 3, st);
+	prof_mark(ws, 4, st);
+	if (ws.prof_on) ws.prof_calls++;
+	return cudaSuccess;
 }
 
 }  // namespace voxb

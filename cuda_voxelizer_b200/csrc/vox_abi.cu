@@ -26,6 +26,8 @@ struct HostPath {
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t buf_free[2] = {nullptr, nullptr};
+	bool buf_busy[2] = {false, false};     // a copy out of pinned[b] may still be in flight
+	int next_buf = 0;
 	cudaEvent_t chunk_ready = nullptr;
 };
 HostPath g_hp[kMaxDevices];
@@ -185,17 +187,16 @@ int h2d(HostPath& hp, void* dst, const void* src, size_t bytes, cudaStream_t st)
 	int rc = ensure_pinned(hp);
 	if (rc) return rc;
 	size_t off = 0;
-	int b = 0;
-	bool used[2] = {false, false};
 	while (off < bytes) {
+		const int b = hp.next_buf;
 		const size_t n = bytes - off < hp.pinned_bytes ? bytes - off : hp.pinned_bytes;
-		if (used[b]) CU(cudaEventSynchronize(hp.buf_free[b]));
+		if (hp.buf_busy[b]) CU(cudaEventSynchronize(hp.buf_free[b]));   // also across calls: the staging buffers are shared
 		memcpy(hp.pinned[b], (const char*)src + off, n);
 		CU(cudaMemcpyAsync((char*)dst + off, hp.pinned[b], n, cudaMemcpyHostToDevice, st));
 		CU(cudaEventRecord(hp.buf_free[b], st));
-		used[b] = true;
+		hp.buf_busy[b] = true;
 		off += n;
-		b ^= 1;
+		hp.next_buf ^= 1;
 	}
 	return VOXB200_OK;
 }
@@ -466,6 +467,32 @@ uint64_t voxb200_launch_count(int reset) {
 	const uint64_t v = g_launch_count;
 	if (reset) g_launch_count = 0;
 	return v;
+}
+
+int voxb200_set_profiling(int on) {
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	if (on && !ws->prof_ev) {
+		ws->prof_ev = new cudaEvent_t[kProfRing][kProfEvents];
+		for (int i = 0; i < kProfRing; i++)
+			for (int k = 0; k < kProfEvents; k++) CU(cudaEventCreate(&ws->prof_ev[i][k]));
+	}
+	ws->prof_on = on != 0;
+	ws->prof_calls = 0;
+	return VOXB200_OK;
+}
+
+int voxb200_phase_ms(unsigned int call_index, float out[4]) {
+	if (!out) return fail(VOXB200_EINVAL, "out is NULL");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	if (!ws->prof_ev || call_index >= ws->prof_calls || ws->prof_calls - call_index > (unsigned)kProfRing)
+		return fail(VOXB200_EINVAL, "call %u is not in the profiling ring (%u calls recorded, ring of %d)", call_index, ws->prof_calls, kProfRing);
+	cudaEvent_t* ev = ws->prof_ev[call_index % kProfRing];
+	for (int k = 0; k < 4; k++) CU(cudaEventElapsedTime(&out[k], ev[k], ev[k + 1]));
+	return VOXB200_OK;
 }
 
 int voxb200_last_counters(uint64_t out[4]) {

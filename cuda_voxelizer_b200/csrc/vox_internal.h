@@ -6,6 +6,9 @@
 
 namespace voxb {
 
+constexpr int kProfRing = 256;     // calls remembered
+constexpr int kProfEvents = 5;     // start | zero done | per-triangle kernel done | cooperative kernel done | scan done
+
 // Device scratch owned by the library, one per device, grown on demand (never shrunk).
 struct Workspace {
 	int device = -1;
@@ -15,7 +18,16 @@ struct Workspace {
 	size_t queue_cap = 0;                     // entries
 	unsigned int* scratch = nullptr;          // solid: mark table for ACCUMULATE / morton modes
 	size_t scratch_words = 0;
+	// optional per-phase timing (voxb200_set_profiling): a ring of event sets, one set per call
+	bool prof_on = false;
+	unsigned int prof_calls = 0;
+	cudaEvent_t (*prof_ev)[kProfEvents] = nullptr;    // [kProfRing][kProfEvents]
 };
+
+// Records phase boundary `which` of the current call on `st` when profiling is on.
+inline void prof_mark(Workspace& ws, int which, cudaStream_t st) {
+	if (ws.prof_on && ws.prof_ev) cudaEventRecord(ws.prof_ev[ws.prof_calls % kProfRing][which], st);
+}
 
 enum Counter {
 	kCtrQueue = 0,        // packed: (queue entries << 32) | work items

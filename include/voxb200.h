@@ -141,6 +141,15 @@ uint64_t voxb200_launch_count(int reset);
  * [0] triangles routed to the cooperative (large-triangle) path, [1] work items of that path,
  * [2] solid: samples clamped because xmax fell outside [0, G-1] (reference UB territory). */
 int voxb200_last_counters(uint64_t out[4]);
+/*
+ * Per-phase device timing.  With profiling on, every voxb200_surface / voxb200_solid call records CUDA
+ * events on its own stream between its kernels (a ring of the last 256 calls).  After the stream has
+ * been synchronised, voxb200_phase_ms(i, out) gives, for the i-th call since profiling was enabled,
+ * milliseconds of: [0] table zero-fill, [1] per-triangle kernel, [2] cooperative (large-triangle)
+ * kernel, [3] solid column scan (0 for surface).
+ */
+int voxb200_set_profiling(int on);
+int voxb200_phase_ms(unsigned int call_index, float out[4]);
 const char* voxb200_version(void);
 
 #ifdef __cplusplus

@@ -190,6 +190,32 @@ def test_empty_and_degenerate_inputs(vb):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("g", [32, 64, 256])
+def test_tiny_and_degenerate_triangles(vb, g):
+    """Triangles no larger than ~2 voxels (the branch-free <=3x3x3 path), including zero-area ones whose
+    normal is NaN, points, collinear triples and triangles hugging the grid boundary."""
+    rng = np.random.default_rng(123 + g)
+    n = 6000
+    unit = 1.0 / g
+    c = rng.uniform(0.0, 1.0, (n, 1, 3))
+    t = c + rng.uniform(-1.0, 1.0, (n, 3, 3)) * unit * rng.choice([0.05, 0.5, 1.0], (n, 1, 1))
+    t[0:500, 1] = t[0:500, 0]                                   # two equal vertices
+    t[500:1000, 1] = t[500:1000, 0]; t[500:1000, 2] = t[500:1000, 0]   # a point
+    t[1000:1500, 2] = 2 * t[1000:1500, 1] - t[1000:1500, 0]     # collinear
+    t[1500:2000, :, 0] = np.round(t[1500:2000, :, 0] * g) / g   # vertices exactly on voxel faces in x
+    t[2000:2500, :, 2] = t[2000:2500, 0:1, 2]                   # axis-aligned in z
+    soup = np.clip(t, 0.0, 1.0).reshape(n, 9).astype(np.float32)
+    soup[-1] = [0, 0, 0, 1, 0, 0, 0, 1, 0]                      # keeps the bbox at the unit cube
+    soup[-2] = [1, 1, 1, 0, 1, 1, 1, 0, 1]
+    grid = vb.grid_from_verts(soup.reshape(-1, 3), g, n)
+    bb_min, un = np.array(grid.bbox_min[:], np.float32), np.array(grid.unit[:], np.float32)
+    d = torch.from_numpy(soup).cuda()
+    for morton in (False, True):
+        got = vb.voxelize(grid, d, morton=morton).cpu().numpy().view(np.uint32)
+        want = oracle.surface(soup, bb_min, un, g, morton)
+        assert np.array_equal(got, want), "morton=%s differing words %s" % (morton, np.nonzero(got ^ want)[0][:8])
+
+
 def test_invalid_arguments_report_einval(vb):
     from cuda_voxelizer_b200 import _lib
     grid = vb.make_grid([0, 0, 0], [1, 1, 1], 48, 1)
