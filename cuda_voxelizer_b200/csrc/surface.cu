@@ -1,22 +1,32 @@
 // surface.cu — surface voxelization for sm_100a (replaces voxelize.cu:58-238 of the reference).
 //
-// Schedule (one stream, no host synchronisation):
-//   zero_kernel            the region's table bytes, 16-byte stores           (skipped with ACCUMULATE)
-//   surface_tri_kernel     one thread per triangle: coalesced fetch, exact setup, grid bbox.  Triangles
-//                          with at most kSmallMax candidate voxels are finished by their thread (word-run
-//                          aggregated atomicOr); bigger ones are queued with a warp-aggregated reservation
-//                          of {queue slot, work-item range} through ONE packed 64-bit atomic per warp.
-//   surface_coop_kernel    persistent grid; each warp takes work items = (queued triangle, block of
-//                          kRowsPerItem (y,z) rows).  Rows failing the x-independent YZ edge tests are skipped
-//                          whole; the rest are swept 32 x at a time, lanes across x, so a table word is built
-//                          by one __ballot_sync and written by one atomicOr.
+// Schedule (one stream, no host synchronisation anywhere):
+//   zero_kernel          the region's table bytes, 16-byte stores                       (skipped with ACCUMULATE)
+//   surface_tri_kernel   one warp per tile of 32 consecutive triangles.  The tile's 1152 bytes come in with
+//                        16-byte cp.async copies into a warp-private shared slab, each lane takes one triangle:
+//                        exact setup, grid bbox, then
+//                          - bbox <= 3x3x3 ("micro", the regime of meshes tessellated near the voxel size):
+//                            all 27 candidates in branch-free straight-line code -> 27-bit hit mask, written
+//                            one (y,z) row (3 x-adjacent bits) per atomicOr;
+//                          - up to kSmallMax candidates: per-thread loop with word-run aggregation;
+//                          - anything bigger: queued for the cooperative kernel ({slot, work items} reserved
+//                            with ONE packed 64-bit atomic per warp).
+//   surface_coop_kernel  persistent grid; a warp takes (queued triangle, block of kRowsPerItem (y,z) rows),
+//                        skips rows failing the x-independent YZ tests, sweeps the rest 32 x at a time, lanes
+//                        across x: one __ballot_sync builds a table word, one atomicOr writes it.
+//
+// Measured and rejected on B200 (10M-triangle mesh @2048^3, profiles/README.md): a persistent per-triangle grid
+// (static stride or ticket counter: +50 % time, DRAM re-reads double); parking results while the zero-fill
+// drains and writing them from a second launch (the atomics, no longer hidden under arithmetic, cost what the
+// overlap saved); staging table words in a shared-memory hash per block (+65 %).
 //
 // Every voxel that is set passed the reference's exact per-voxel expression sequence (vox_exact.cuh).
 #include "vox_internal.h"
 
 namespace voxb {
 
-constexpr int kBlock = 256;
+constexpr int kBlock = 256;        // cooperative kernel
+constexpr int kTriBlock = 128;     // per-triangle kernel: 4 warps, each with its own staging slab
 constexpr int kSmallMax = 64;      // candidate voxels a single thread finishes itself
 constexpr int kRowsPerItem = 32;   // (y,z) rows per cooperative work item
 
@@ -73,8 +83,7 @@ __device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {   
 	return __funnelshift_l(__float_as_uint(v), mask, 1);
 }
 
-template <bool MORTON>
-__device__ __forceinline__ void surf_micro3(const SurfSetup& s, const GridParams& g, unsigned int* __restrict__ table) {
+__device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const GridParams& g) {
 	float px[3], py[3], pz[3];
 #pragma unroll
 	for (int i = 0; i < 3; i++) {
@@ -158,26 +167,54 @@ __device__ __forceinline__ void surf_micro3(const SurfSetup& s, const GridParams
 	const unsigned int zx27 = zx_s * 0x49u;                                             // copies at +0, +3, +6
 	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..2
 	const unsigned int valid = (((2u << ex) - 1u) * 0x1249249u) & (((8u << (3 * ey)) - 1u) * 0x40201u) & ((512u << (9 * ez)) - 1u);
-	unsigned int hit = valid & ~(rej | xy27 | yz27 | zx27);
+	return valid & ~(rej | xy27 | yz27 | zx27);
+}
 
+// Writes a 27-bit hit mask (bit i + 3j + 9k = voxel (x0+i, y0+j, z0+k)) into the table: one (y,z) row — three
+// x-adjacent bits — at a time, as one atomicOr, or two when the row straddles a word.
+template <bool MORTON>
+__device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, int z0, const GridParams& g,
+                                              unsigned int* __restrict__ table) {
 	if (MORTON) {
-		WordRun<false> run;
+		unsigned long long cur = ~0ull;
+		unsigned int mask = 0u;
 		while (hit) {
 			const int b = __ffs(hit) - 1;
 			hit &= hit - 1u;
 			const int k = b / 9, j = (b - 9 * k) / 3, i = b - 9 * k - 3 * j;
-			run.add(table, g, morton3((unsigned)(s.x0 + i), (unsigned)(s.y0 + j), (unsigned)(s.z0 + k)));
+			const unsigned long long idx = morton3((unsigned)(x0 + i), (unsigned)(y0 + j), (unsigned)(z0 + k));
+			const unsigned long long w = (idx >> 5) - g.word_base;
+			if (w != cur) { if (mask) atomicOr(table + cur, mask); cur = w; mask = 0u; }
+			mask |= 1u << (31u - (unsigned int)(idx & 31ull));
 		}
-		run.flush(table);
+		if (mask) atomicOr(table + cur, mask);
+		return;
+	}
+	if ((g.G & 31) == 0 && g.G <= 4096) {
+		// rows are whole words and every word offset fits 32 bits: all-integer-32 addressing
+		const unsigned int Gw = (unsigned int)g.G >> 5;
+		const unsigned int w0 = Gw * ((unsigned int)y0 + (unsigned int)g.G * (unsigned int)z0) + ((unsigned int)x0 >> 5) - (unsigned int)g.word_base;
+		const unsigned int sh = (unsigned int)x0 & 31u;
+		while (hit) {
+			const int r = (__ffs(hit) - 1) / 3;                    // row = j + 3k
+			const unsigned int bits = (hit >> (3 * r)) & 7u;        // x0, x0+1, x0+2
+			hit &= ~(7u << (3 * r));
+			const int k = r / 3, j = r - 3 * k;
+			const unsigned int w = w0 + Gw * ((unsigned int)j + (unsigned int)g.G * (unsigned int)k);
+			const unsigned int v = __brev(bits);                    // x0 -> bit 31, x0+1 -> 30, x0+2 -> 29
+			const unsigned int hi = v >> sh, lo = __funnelshift_r(0u, v, sh);
+			if (hi) atomicOr(table + w, hi);
+			if (lo) atomicOr(table + w + 1, lo);
+		}
 		return;
 	}
 	const unsigned long long G = (unsigned long long)g.G;
 	while (hit) {
-		const int r = (__ffs(hit) - 1) / 3;                    // row = j + 3k
-		const unsigned int bits = (hit >> (3 * r)) & 7u;        // x0, x0+1, x0+2
+		const int r = (__ffs(hit) - 1) / 3;
+		const unsigned int bits = (hit >> (3 * r)) & 7u;
 		hit &= ~(7u << (3 * r));
 		const int k = r / 3, j = r - 3 * k;
-		const unsigned long long idx = (unsigned long long)s.x0 + G * ((unsigned long long)(s.y0 + j) + G * (unsigned long long)(s.z0 + k));
+		const unsigned long long idx = (unsigned long long)x0 + G * ((unsigned long long)(y0 + j) + G * (unsigned long long)(z0 + k));
 		// voxel idx+t sits at bit 31-((idx+t)&31): put the row MSB-first into a 64-bit window over words w, w+1
 		const unsigned long long win = ((unsigned long long)(__brev(bits) >> 29) << 61) >> (unsigned int)(idx & 31ull);
 		const unsigned long long w = (idx >> 5) - g.word_base;
@@ -187,44 +224,65 @@ __device__ __forceinline__ void surf_micro3(const SurfSetup& s, const GridParams
 	}
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+	const unsigned int d = (unsigned int)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
 template <bool MORTON, bool SOA4>
-__global__ void __launch_bounds__(kBlock) surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
-                                                             unsigned int* __restrict__ table,
-                                                             unsigned long long* __restrict__ counters,
-                                                             uint2* __restrict__ queue) {
-	__shared__ __align__(16) float stage[SOA4 ? 4 : kBlock * 9];
-	const unsigned long long block_first = (unsigned long long)blockIdx.x * kBlock;
-	const unsigned long long i = block_first + threadIdx.x;
+__global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
+                                                                unsigned int* __restrict__ table,
+                                                                unsigned long long* __restrict__ counters,
+                                                                uint2* __restrict__ queue) {
+	__shared__ __align__(16) float stage[SOA4 ? 4 : (kTriBlock / 32) * 288];
+	const int lane = threadIdx.x & 31;
+	const unsigned long long tile = ((unsigned long long)blockIdx.x * kTriBlock + threadIdx.x) >> 5;
+	const unsigned long long i = (tile << 5) + lane;
+	const bool valid = i < g.n_tris;
+	const bool vec_ok = !SOA4 && (tile << 5) + 32ull <= g.n_tris && (reinterpret_cast<uintptr_t>(tris) & 15u) == 0;
+	float* my_stage = stage + (SOA4 ? 0 : (threadIdx.x >> 5) * 288);
 	Tri t;
-	bool valid;
 	if (SOA4) {
-		valid = i < g.n_tris;
 		if (valid) load_tri_soa4(tris, g.n_tris, i, t);
-	} else {
-		load_tri_block_aos<kBlock>(tris, g.n_tris, block_first, stage, t, valid);
+	} else if (vec_ok) {
+		const float4* src = reinterpret_cast<const float4*>(tris) + tile * 72ull;
+		float4* dst = reinterpret_cast<float4*>(my_stage);
+		cp_async16(dst + lane, src + lane);
+		cp_async16(dst + 32 + lane, src + 32 + lane);
+		if (lane < 8) cp_async16(dst + 64 + lane, src + 64 + lane);
+		cp_async_wait_all();
+		__syncwarp();
+		const float* p = my_stage + 9 * lane;
+		t.v0x = p[0]; t.v0y = p[1]; t.v0z = p[2];
+		t.v1x = p[3]; t.v1y = p[4]; t.v1z = p[5];
+		t.v2x = p[6]; t.v2y = p[7]; t.v2z = p[8];
+	} else if (valid) {
+		load_tri_aos(tris, i, t);
 	}
+
 	SurfSetup s;
-	bool live = false;
+	bool live = false, big = false, micro = false;
 	unsigned int items = 0u;
-	bool big = false;
 	if (valid) {
 		shift_tri(t, g);
 		surf_setup(t, g, s);
 		live = clip_to_region(g, s);
 		if (live) {
-			const long long rows = (long long)(s.y1 - s.y0 + 1) * (long long)(s.z1 - s.z0 + 1);
-			const long long cands = rows * (long long)(s.x1 - s.x0 + 1);
-			big = cands > kSmallMax;
+			const int dx = s.x1 - s.x0, dy = s.y1 - s.y0, dz = s.z1 - s.z0;
+			micro = dx <= 2 && dy <= 2 && dz <= 2;
+			const unsigned long long rows = (unsigned long long)(dy + 1) * (unsigned long long)(dz + 1);
+			big = !micro && rows * (unsigned long long)(dx + 1) > (unsigned long long)kSmallMax;
 			items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
 		}
 	}
 	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
 	if (!live || big) return;
-	if (s.x1 - s.x0 <= 2 && s.y1 - s.y0 <= 2 && s.z1 - s.z0 <= 2) {
-		surf_micro3<MORTON>(s, g, table);
+	if (micro) {
+		const unsigned int hit = surf_micro3(s, g);
+		if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
 		return;
 	}
-
 	WordRun<false> run;
 	for (int z = s.z0; z <= s.z1; z++) {
 		for (int y = s.y0; y <= s.y1; y++) {
@@ -296,12 +354,13 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 // ------------------------------------------------------------------------------------------------
 template <bool MORTON, bool SOA4>
 static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table, cudaStream_t st) {
-	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
-	surface_tri_kernel<MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
+	const unsigned long long tiles = (g.n_tris + 31ull) / 32ull;
+	const unsigned long long blocks = (tiles + (kTriBlock / 32) - 1) / (kTriBlock / 32);
+	surface_tri_kernel<MORTON, SOA4><<<(unsigned)blocks, kTriBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
 	g_launch_count++;
-	prof_mark(ws, 2, st);
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
+	prof_mark(ws, 2, st);
 	static int per_sm = 0;
 	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
