@@ -120,41 +120,73 @@ __global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, 
 	}
 }
 
-// Suffix-XOR along x of every row.  One lane per word; rows are `seg` (= G/32, a power of two) words
-// long.  K = words per lane-column when a row is longer than a warp (seg = 32*K), processed from the
-// row's last 32-word chunk to its first with the parity carried across chunks.
-template <int K, bool XOR_INTO>
-__global__ void __launch_bounds__(kBlock) solid_scan_kernel(const unsigned int* __restrict__ marks,
-                                                            unsigned int* __restrict__ out, size_t n_words, int seg) {
-	const int lane = threadIdx.x & 31;
-	const size_t warp = ((size_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
-	const size_t base = warp * (size_t)(32 * K);
-	if (base >= n_words) return;           // n_words is a multiple of 32*K when K > 1, of seg when K == 1
-	const int width = K > 1 ? 32 : seg;    // lanes per row segment
-	const int pos = lane & (width - 1);
-	unsigned int w[K];
+// Suffix-XOR along x of every row, one lane per word: rows of `seg` = G/32 <= 32 words (a power of two).  Used for
+// G = 32, 64 (rows shorter than 16 bytes) and as the fallback when a table pointer is not 16-byte aligned.
+template <bool XOR_INTO>
+__global__ void __launch_bounds__(kBlock) solid_scan_narrow_kernel(const unsigned int* __restrict__ marks,
+                                                                   unsigned int* __restrict__ out, size_t n_words, int seg) {
+	const size_t at = (size_t)blockIdx.x * kBlock + threadIdx.x;
+	const int pos = (int)(threadIdx.x & 31) & (seg - 1);
+	const unsigned int w = at < n_words ? marks[at] : 0u;
+	unsigned int v = w;
+	v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
+	const unsigned int par = __popc(w) & 1u;
+	unsigned int suf = par;
 #pragma unroll
-	for (int c = 0; c < K; c++) {
-		const size_t at = base + (size_t)c * 32 + lane;
-		w[c] = at < n_words ? marks[at] : 0u;
+	for (int d = 1; d < 32; d <<= 1) {
+		const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
+		if (pos + d < seg) suf ^= dn;
 	}
-	unsigned int carry = 0u;               // parity of all later chunks of this row (uniform per segment)
+	if (suf ^ par) v = ~v;
+	if (at < n_words) out[at] = XOR_INTO ? (out[at] ^ v) : v;
+}
+
+// Suffix-XOR along x of every row, rows of at least 4 words (G >= 128).  A lane owns 4 consecutive words (one
+// 16-byte load and store), a row is `lanes_per_row` = G/128 <= 32 consecutive lanes of a warp (G <= 4096).
+// kScanUnroll independent row groups per thread keep enough 16-byte requests in flight to stream at HBM speed.
+constexpr int kScanUnroll = 4;
+template <bool XOR_INTO>
+__global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restrict__ marks, uint4* __restrict__ out,
+                                                            size_t n_vec, int lanes_per_row) {
+	const int lane = threadIdx.x & 31;
+	const int width = lanes_per_row;                              // lanes of this warp that share a row (<= 32)
+	const int pos = lane & (width - 1);
+	// a warp owns kScanUnroll consecutive 32-lane spans
+	const size_t warp = ((size_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+	const size_t span0 = warp * (size_t)kScanUnroll;
+	{
+		uint4 m[kScanUnroll];
 #pragma unroll
-	for (int c = K - 1; c >= 0; c--) {
-		unsigned int v = w[c];
-		v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
-		const unsigned int par = __popc(w[c]) & 1u;
-		unsigned int suf = par;            // inclusive suffix parity over lanes of the segment
-#pragma unroll
-		for (int d = 1; d < 32; d <<= 1) {
-			const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
-			if (d < width && pos + d < width) suf ^= dn;
+		for (int u = 0; u < kScanUnroll; u++) {
+			const size_t at = (span0 + u) * 32 + lane;
+			m[u] = at < n_vec ? __ldg(marks + at) : make_uint4(0u, 0u, 0u, 0u);
 		}
-		const unsigned int later = (suf ^ par) ^ carry;      // words after mine in this row
-		if (later) v = ~v;
-		const size_t at = base + (size_t)c * 32 + lane;
-		if (at < n_words) out[at] = XOR_INTO ? (out[at] ^ v) : v;
-		if (K > 1) carry ^= __shfl_sync(0xffffffffu, suf, 0);   // whole-chunk parity
+#pragma unroll
+		for (int u = 0; u < kScanUnroll; u++) {
+			const size_t at = (span0 + u) * 32 + lane;
+			unsigned int w[4] = {m[u].x, m[u].y, m[u].z, m[u].w};
+			const unsigned int par = (__popc(w[0]) + __popc(w[1]) + __popc(w[2]) + __popc(w[3])) & 1u;
+			unsigned int suf = par;                          // inclusive suffix parity over the row's lanes
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
+				if (d < width && pos + d < width) suf ^= dn;
+			}
+			unsigned int carry = suf ^ par;                  // parity of everything after this lane's 4 words
+#pragma unroll
+			for (int c = 3; c >= 0; c--) {
+				unsigned int v = w[c];
+				v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
+				if (carry) v = ~v;
+				carry ^= __popc(w[c]) & 1u;
+				w[c] = v;
+			}
+			if (at < n_vec) {
+				uint4 r = make_uint4(w[0], w[1], w[2], w[3]);
+				if (XOR_INTO) { const uint4 o = out[at]; r.x ^= o.x; r.y ^= o.y; r.z ^= o.z; r.w ^= o.w; }
+				out[at] = r;
+			}
+		}
 	}
 }
 
@@ -178,15 +210,18 @@ static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const flo
 
 template <bool XOR_INTO>
 static cudaError_t run_scan(const unsigned int* marks, unsigned int* out, size_t n_words, int seg, cudaStream_t st) {
-	const int k = seg <= 32 ? 1 : seg / 32;
-	const size_t warps = (n_words + (size_t)32 * k - 1) / ((size_t)32 * k);
-	const unsigned int blocks = (unsigned int)((warps + (kBlock / 32) - 1) / (kBlock / 32));
-	switch (k) {
-		case 1: solid_scan_kernel<1, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
-		case 2: solid_scan_kernel<2, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
-		case 4: solid_scan_kernel<4, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
-		case 8: solid_scan_kernel<8, XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg); break;
-		default: return cudaErrorInvalidValue;
+	const bool vec = seg >= 4 && (n_words & 3u) == 0 && ((reinterpret_cast<uintptr_t>(marks) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0;
+	if (!vec) {
+		if (seg > 32) return cudaErrorInvalidValue;         // G >= 2048 needs a 16-byte aligned table
+		const unsigned int blocks = (unsigned int)((n_words + kBlock - 1) / kBlock);
+		solid_scan_narrow_kernel<XOR_INTO><<<blocks, kBlock, 0, st>>>(marks, out, n_words, seg);
+	} else {
+		const size_t n_vec = n_words / 4;
+		const int lanes_per_row = seg / 4;
+		const size_t spans = (n_vec + 31) / 32;
+		const size_t warps = (spans + (size_t)kScanUnroll - 1) / (size_t)kScanUnroll;
+		const unsigned int blocks = (unsigned int)((warps + (kBlock / 32) - 1) / (kBlock / 32));
+		solid_scan_kernel<XOR_INTO><<<blocks, kBlock, 0, st>>>(reinterpret_cast<const uint4*>(marks), reinterpret_cast<uint4*>(out), n_vec, lanes_per_row);
 	}
 	g_launch_count++;
 	return cudaGetLastError();
@@ -198,7 +233,7 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris
 	if (err != cudaSuccess) return err;
 	const bool pow2 = (g.G & (g.G - 1)) == 0;
 	const bool full_xy = g.rx0 == 0 && g.rx1 == g.G && g.ry0 == 0 && g.ry1 == g.G;
-	const bool scan = !o.morton && pow2 && g.G >= 32 && g.G <= 8192 && full_xy;
+	const bool scan = !o.morton && pow2 && g.G >= 32 && g.G <= 4096 && full_xy;
 	unsigned int* marks = d_table;
 	if (scan && o.accumulate) {
 		// marks must start from zero: stage them in library scratch and XOR the scanned rows into the table

@@ -8,12 +8,15 @@
 //                          - bbox <= 3x3x3 ("micro", the regime of meshes tessellated near the voxel size):
 //                            all 27 candidates in branch-free straight-line code -> 27-bit hit mask, written
 //                            one (y,z) row (3 x-adjacent bits) per atomicOr;
-//                          - up to kSmallMax candidates: per-thread loop with word-run aggregation;
 //                          - anything bigger: queued for the cooperative kernel ({slot, work items} reserved
 //                            with ONE packed 64-bit atomic per warp).
-//   surface_coop_kernel  persistent grid; a warp takes (queued triangle, block of kRowsPerItem (y,z) rows),
-//                        skips rows failing the x-independent YZ tests, sweeps the rest 32 x at a time, lanes
-//                        across x: one __ballot_sync builds a table word, one atomicOr writes it.
+//   surface_coop_kernel  persistent grid over work items = (queued triangle, kRowsPerItem consecutive (y,z) rows);
+//                        8 lanes per item, ONE LANE PER ROW.  A row failing the x-independent YZ tests is dropped;
+//                        otherwise the lane SOLVES the row instead of sweeping it: every remaining test is a
+//                        monotone function of x (rounding, int->float and multiplying/adding a constant all
+//                        preserve order), so the accepted voxels of a row form one interval whose two ends are
+//                        found by bisection on the reference's exact expressions — O(log width) evaluations
+//                        instead of width — and written as whole-word masks.
 //
 // Measured and rejected on B200 (10M-triangle mesh @2048^3, profiles/README.md): a persistent per-triangle grid
 // (static stride or ticket counter: +50 % time, DRAM re-reads double); parking results while the zero-fill
@@ -27,8 +30,7 @@ namespace voxb {
 
 constexpr int kBlock = 256;        // cooperative kernel
 constexpr int kTriBlock = 128;     // per-triangle kernel: 4 warps, each with its own staging slab
-constexpr int kSmallMax = 64;      // candidate voxels a single thread finishes itself
-constexpr int kRowsPerItem = 32;   // (y,z) rows per cooperative work item
+constexpr int kRowsPerItem = 8;    // (y,z) rows per cooperative work item: one per lane of an 8-lane group
 
 unsigned long long g_launch_count = 0;
 
@@ -272,27 +274,78 @@ __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams
 			const int dx = s.x1 - s.x0, dy = s.y1 - s.y0, dz = s.z1 - s.z0;
 			micro = dx <= 2 && dy <= 2 && dz <= 2;
 			const unsigned long long rows = (unsigned long long)(dy + 1) * (unsigned long long)(dz + 1);
-			big = !micro && rows * (unsigned long long)(dx + 1) > (unsigned long long)kSmallMax;
+			big = !micro;
 			items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
 		}
 	}
 	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
 	if (!live || big) return;
-	if (micro) {
-		const unsigned int hit = surf_micro3(s, g);
-		if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
-		return;
+	const unsigned int hit = surf_micro3(s, g);
+	if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Exact row solver.  For a fixed (y,z) row every x-dependent test value is
+//     f(x) = fl(fl(c * fl(float(x) * unit.x)) + row constant ...)
+// i.e. a composition of order-preserving maps of x (int->float conversion, rounding, multiplication by a
+// constant, addition of a constant), hence weakly monotone in x with the direction given by the sign of c.
+// So each test accepts a half-line of x (an interval for the plane test), and the exact end points follow from
+// bisection with the reference expression itself as the predicate — no error analysis, no tolerance.
+// ------------------------------------------------------------------------------------------------
+// smallest x in [lo, hi] with pred(x) true, or hi + 1; pred must be false...false true...true on [lo, hi]
+template <typename Pred>
+__device__ __forceinline__ int first_true(int lo, int hi, Pred pred) {
+	int L = lo, H = hi + 1;
+	while (L < H) {
+		const int mid = (L + H) >> 1;
+		if (pred(mid)) H = mid; else L = mid + 1;
 	}
-	WordRun<false> run;
-	for (int z = s.z0; z <= s.z1; z++) {
-		for (int y = s.y0; y <= s.y1; y++) {
-			SurfRow row;
-			if (!surf_row(s, g, y, z, row)) continue;
-			for (int x = s.x0; x <= s.x1; x++)
-				if (surf_voxel(s, g, row, x)) run.add(table, g, voxel_index<MORTON>(g, x, y, z));
-		}
+	return L;
+}
+// largest x in [lo, hi] with pred(x) true, or lo - 1; pred must be true...true false...false on [lo, hi]
+template <typename Pred>
+__device__ __forceinline__ int last_true(int lo, int hi, Pred pred) {
+	return first_true(lo, hi, [&](int x) { return !pred(x); }) - 1;
+}
+// Narrow [lo, hi] to the x accepted by `acc`, which is monotone in x with direction sign(coef):
+// coef > 0: rejected...accepted; coef < 0: accepted...rejected; otherwise constant in x.
+template <typename Acc>
+__device__ __forceinline__ void narrow(int& lo, int& hi, float coef, Acc acc) {
+	if (lo > hi) return;
+	if (coef > 0.0f) lo = first_true(lo, hi, acc);
+	else if (coef < 0.0f) hi = last_true(lo, hi, acc);
+	else if (!acc(lo)) hi = lo - 1;
+}
+
+// Accepted x-interval [lo, hi] of row (y,z) (empty when lo > hi); s.x0..s.x1 is the triangle's clipped bbox.
+__device__ __forceinline__ void surf_solve_row(const SurfSetup& s, const GridParams& g, const SurfRow& r, int& lo, int& hi) {
+	lo = s.x0; hi = s.x1;
+	// plane (cpu_voxelizer.cpp:139-140): rejected iff P = (n.p + d1)(n.p + d2) > 0, i.e. both factors strictly on the
+	// same side (and the product not underflowing to 0).  n.p moves with sign(n.x): the "both below" rejections are
+	// closed towards one end of the row and the "both above" ones towards the other.
+	auto plane = [&](int x, bool& below) {
+		const float px = fmul((float)x, g.ux);
+		const float ndp = fadd(fadd(fmul(s.nx, px), r.ny_py), r.nz_pz);
+		const float a = fadd(ndp, s.d1);
+		below = a < 0.0f;
+		return fmul(a, fadd(ndp, s.d2)) > 0.0f;       // true = rejected
+	};
+	if (s.nx > 0.0f) {
+		lo = first_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && b); });
+		if (lo <= hi) hi = last_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && !b); });
+	} else if (s.nx < 0.0f) {
+		lo = first_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && !b); });
+		if (lo <= hi) hi = last_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && b); });
+	} else {
+		bool b;
+		if (plane(lo, b)) hi = lo - 1;                // n.x is 0 or NaN: the test does not depend on x
 	}
-	run.flush(table);
+#pragma unroll
+	for (int k = 0; k < 3; k++)                        // XY edges (:144-147): value moves with sign(n_xy_e.x)
+		narrow(lo, hi, s.xy_a[k], [&](int x) { return !(fadd(fadd(fmul(s.xy_a[k], fmul((float)x, g.ux)), r.xy_bpy[k]), s.xy_d[k]) < 0.0f); });
+#pragma unroll
+	for (int k = 0; k < 3; k++)                        // ZX edges (:156-159): value moves with sign(n_zx_e.y)
+		narrow(lo, hi, s.zx_b[k], [&](int x) { return !(fadd(fadd(r.zx_apz[k], fmul(s.zx_b[k], fmul((float)x, g.ux))), s.zx_d[k]) < 0.0f); });
 }
 
 template <bool MORTON, bool SOA4>
@@ -303,18 +356,18 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 	const unsigned long long packed = counters[kCtrQueue];
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_items = (unsigned int)packed;
-	const int lane = threadIdx.x & 31;
-	const unsigned int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
-	const unsigned int n_warps = (gridDim.x * kBlock) >> 5;
+	const int sub = threadIdx.x & (kRowsPerItem - 1);                       // my row within the item
+	const unsigned int group = (blockIdx.x * kBlock + threadIdx.x) / kRowsPerItem;
+	const unsigned int n_groups = (gridDim.x * kBlock) / kRowsPerItem;
 	const bool aligned = (g.G & 31) == 0;
 
-	for (unsigned int item = warp; item < n_items; item += n_warps) {
-		unsigned int lo = 0u, hi = n_entries - 1u;
-		while (lo < hi) {
-			const unsigned int mid = (lo + hi + 1u) >> 1;
-			if (__ldg(&queue[mid].y) <= item) lo = mid; else hi = mid - 1u;
+	for (unsigned int item = group; item < n_items; item += n_groups) {
+		unsigned int lo_e = 0u, hi_e = n_entries - 1u;                      // last entry whose first item <= item
+		while (lo_e < hi_e) {
+			const unsigned int mid = (lo_e + hi_e + 1u) >> 1;
+			if (__ldg(&queue[mid].y) <= item) lo_e = mid; else hi_e = mid - 1u;
 		}
-		const uint2 e = __ldg(&queue[lo]);
+		const uint2 e = __ldg(&queue[lo_e]);
 		Tri t;
 		if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
 		shift_tri(t, g);
@@ -323,29 +376,29 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 		clip_to_region(g, s);
 		const int ny = s.y1 - s.y0 + 1;
 		const long long rows = (long long)ny * (long long)(s.z1 - s.z0 + 1);
-		const long long r0 = (long long)(item - e.y) * kRowsPerItem;
-		const long long r1 = min(rows, r0 + (long long)kRowsPerItem);
-		for (long long r = r0; r < r1; r++) {
-			const int z = s.z0 + (int)(r / ny), y = s.y0 + (int)(r % ny);
-			SurfRow row;
-			if (!surf_row(s, g, y, z, row)) continue;
-			const unsigned long long row_idx = MORTON ? 0ull : (unsigned long long)g.G * ((unsigned long long)y + (unsigned long long)g.G * (unsigned long long)z);
-			for (int xb = s.x0 & ~31; xb <= s.x1; xb += 32) {
-				const int x = xb + lane;
-				const bool hit = (x >= s.x0) && (x <= s.x1) && surf_voxel(s, g, row, x);
-				if (MORTON) {
-					const unsigned long long idx = morton3((unsigned)x, (unsigned)y, (unsigned)z);
-					unsigned int m = hit ? (1u << (31u - (unsigned int)(idx & 31ull))) : 0u;
-					m |= __shfl_xor_sync(0xffffffffu, m, 1);     // 4 consecutive x share one morton word
-					m |= __shfl_xor_sync(0xffffffffu, m, 2);
-					if ((lane & 3) == 0 && m) atomicOr(table + ((idx >> 5) - g.word_base), m);
-				} else if (aligned) {
-					const unsigned int b = __ballot_sync(0xffffffffu, hit);
-					if (lane == 0 && b) atomicOr(table + (((row_idx + (unsigned long long)xb) >> 5) - g.word_base), __brev(b));
-				} else if (hit) {
-					const unsigned long long idx = row_idx + (unsigned long long)x;
-					atomicOr(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
-				}
+		const long long r = (long long)(item - e.y) * kRowsPerItem + sub;
+		if (r >= rows) continue;
+		const int z = s.z0 + (int)(r / ny), y = s.y0 + (int)(r % ny);
+		SurfRow row;
+		if (!surf_row(s, g, y, z, row)) continue;
+		int xa, xb;
+		surf_solve_row(s, g, row, xa, xb);
+		if (xa > xb) continue;
+		if (MORTON || !aligned) {
+			WordRun<false> run;
+			for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<MORTON>(g, x, y, z));
+			run.flush(table);
+		} else {
+			// rows are whole words: first/last word get partial masks (x at bit 31 - x%32), the middle ones 0xffffffff
+			unsigned int* rowp = table + (((unsigned long long)g.G * ((unsigned long long)y + (unsigned long long)g.G * (unsigned long long)z)) >> 5) - g.word_base;
+			const int wa = xa >> 5, wb = xb >> 5;
+			const unsigned int first = 0xffffffffu >> (xa & 31), last = 0xffffffffu << (31 - (xb & 31));
+			if (wa == wb) {
+				atomicOr(rowp + wa, first & last);
+			} else {
+				atomicOr(rowp + wa, first);
+				for (int w = wa + 1; w < wb; w++) atomicOr(rowp + w, 0xffffffffu);
+				atomicOr(rowp + wb, last);
 			}
 		}
 	}
