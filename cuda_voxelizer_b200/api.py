@@ -82,7 +82,7 @@ def voxelize(grid, tris, table=None, morton=False, region=None, stream=None, acc
     9 floats per triangle (or 3 float4 planes with ``soa4``).  Returns the uint32 bit table as an
     int32 CUDA tensor (the region's words only when ``region`` is given).  Asynchronous on ``stream``."""
     if table is None:
-        table = _new_table(grid, region, morton, tris.device)
+        table = _new_table(grid, region, morton, getattr(tris, "device", "cuda"))
     flags = (MORTON if morton else 0) | (ACCUMULATE if accumulate else 0) | (TRIS_SOA4 if soa4 else 0)
     return _run(_lib.lib().voxb200_surface, grid, tris, table, flags, region, stream)
 
@@ -90,7 +90,7 @@ def voxelize(grid, tris, table=None, morton=False, region=None, stream=None, acc
 def voxelize_solid(grid, tris, table=None, morton=False, region=None, stream=None, accumulate=False, soa4=False):
     """Solid voxelization (reference: voxelize_solid(), voxelize_solid.cu:147)."""
     if table is None:
-        table = _new_table(grid, region, morton, tris.device)
+        table = _new_table(grid, region, morton, getattr(tris, "device", "cuda"))
     flags = (MORTON if morton else 0) | (ACCUMULATE if accumulate else 0) | (TRIS_SOA4 if soa4 else 0)
     return _run(_lib.lib().voxb200_solid, grid, tris, table, flags, region, stream)
 
@@ -175,3 +175,12 @@ def phase_ms(call_index):
     out = (C.c_float * 4)()
     check(_lib.lib().voxb200_phase_ms(int(call_index), out))
     return [float(x) for x in out]
+
+
+def route_triangles(grid, tris, region, solid=False, morton=False, stream=0):
+    """Device-side routing of a 9-float soup to one region (multi-GPU slabs).  Returns (DeviceBuffer, count)."""
+    out = C.c_void_p(0)
+    n = C.c_size_t(0)
+    flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+    check(_lib.lib().voxb200_route_triangles(C.byref(grid), C.c_void_p(tris.data_ptr()), flags, C.byref(region), C.byref(out), C.byref(n), C.c_void_p(stream)))
+    return DeviceBuffer(out.value, n.value * 36), int(n.value)

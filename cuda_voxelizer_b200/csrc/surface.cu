@@ -268,9 +268,13 @@ __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams
 	unsigned int items = 0u;
 	if (valid) {
 		shift_tri(t, g);
-		surf_setup(t, g, s);
-		live = clip_to_region(g, s);
-		if (live) {
+		surf_bbox(t, g, s);
+		live = clip_to_region(g, s);          // triangles of other slabs (multi-GPU regions) stop here
+	}
+	if (!__any_sync(0xffffffffu, live)) return;
+	if (live) {
+		surf_setup_tests(t, g, s);
+		{
 			const int dx = s.x1 - s.x0, dy = s.y1 - s.y0, dz = s.z1 - s.z0;
 			micro = dx <= 2 && dy <= 2 && dz <= 2;
 			const unsigned long long rows = (unsigned long long)(dy + 1) * (unsigned long long)(dz + 1);

@@ -80,6 +80,52 @@ __global__ void bbox_decode_kernel(unsigned int* keys) {
 	}
 }
 
+// Triangle routing for multi-GPU regions: keeps the triangles whose footprint can touch `g`'s
+// region — surface: the clamped grid bbox of voxelize.cu:86-87; solid: the centre-sample (y,z) range of
+// voxelize_solid.cu:112-113 — using the same arithmetic as the voxelization kernels, and appends them to a
+// compact soup through a warp-aggregated cursor.
+template <bool SOLID>
+__global__ void __launch_bounds__(kUpBlock) route_kernel(const GridParams g, const float* __restrict__ soup, float* __restrict__ out,
+                                                         unsigned long long* __restrict__ cursor) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * kUpBlock + threadIdx.x;
+	bool keep = false;
+	Tri t;
+	if (i < g.n_tris) {
+		load_tri_aos(soup, i, t);
+		Tri ts = t;
+		shift_tri(ts, g);
+		if (SOLID) {
+			SolidSetup s;
+			solid_setup(ts, g, s);
+			keep = !s.skip && max(s.y0, g.ry0) <= min(s.y1, g.ry1 - 1) && max(s.z0, g.rz0) <= min(s.z1, g.rz1 - 1);
+		} else {
+			SurfSetup s;
+			surf_bbox(ts, g, s);
+			keep = max(s.x0, g.rx0) <= min(s.x1, g.rx1 - 1) && max(s.y0, g.ry0) <= min(s.y1, g.ry1 - 1) && max(s.z0, g.rz0) <= min(s.z1, g.rz1 - 1);
+		}
+	}
+	const unsigned int m = __ballot_sync(0xffffffffu, keep);
+	if (m == 0u) return;
+	const int lane = threadIdx.x & 31;
+	unsigned long long base = 0ull;
+	if (lane == 0) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+	base = __shfl_sync(0xffffffffu, base, 0);
+	if (keep) {
+		float* o = out + 9ull * (base + __popc(m & ((1u << lane) - 1u)));
+		o[0] = t.v0x; o[1] = t.v0y; o[2] = t.v0z; o[3] = t.v1x; o[4] = t.v1y; o[5] = t.v1z; o[6] = t.v2x; o[7] = t.v2y; o[8] = t.v2z;
+	}
+}
+
+cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st) {
+	cudaError_t err = cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), st);
+	if (err != cudaSuccess || g.n_tris == 0) return err;
+	const unsigned blocks = (unsigned)((g.n_tris + kUpBlock - 1) / kUpBlock);
+	if (solid) route_kernel<true><<<blocks, kUpBlock, 0, st>>>(g, d_soup, d_out, d_cursor);
+	else route_kernel<false><<<blocks, kUpBlock, 0, st>>>(g, d_soup, d_out, d_cursor);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tris, cudaStream_t st) {
 	if (n_tris == 0) return cudaSuccess;
 	soup_to_soa4_kernel<<<(unsigned)((n_tris + kUpBlock - 1) / kUpBlock), kUpBlock, 0, st>>>(d_soup, reinterpret_cast<float4*>(d_soa4), n_tris);

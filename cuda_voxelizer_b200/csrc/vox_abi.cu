@@ -405,6 +405,30 @@ int voxb200_upload_indexed(const float* host_verts, size_t n_verts, const int32_
 	return VOXB200_OK;
 }
 
+int voxb200_route_triangles(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* region,
+                            float** d_routed, size_t* n_routed, void* stream) {
+	if (!grid || !d_routed || !n_routed || (!d_tris9 && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
+	if (flags & VOXB200_TRIS_SOA4) return fail(VOXB200_EINVAL, "routing takes the 9-float soup");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	GridParams g;
+	size_t region_words = 0;
+	rc = resolve_region(grid, region, (flags & VOXB200_MORTON) != 0, &g, &region_words);
+	if (rc) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	float* out = nullptr;
+	CU(cudaMalloc(&out, grid->n_triangles ? grid->n_triangles * 9 * sizeof(float) : 16));
+	cudaError_t e = launch_route(g, (flags & VOXB200_SOLID) != 0, d_tris9, out, ws->counters + kCtrClaim, st);
+	unsigned long long n = 0;
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&n, ws->counters + kCtrClaim, sizeof(n), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) { cudaFree(out); return fail_cuda(e, "voxb200_route_triangles"); }
+	*d_routed = out;
+	*n_routed = (size_t)n;
+	return VOXB200_OK;
+}
+
 int voxb200_surface(const voxb200_grid* grid, const float* d_tris, unsigned int* d_table, unsigned int flags,
                     const voxb200_region* region, void* stream) {
 	return run_path(false, grid, d_tris, d_table, flags, region, (cudaStream_t)stream);

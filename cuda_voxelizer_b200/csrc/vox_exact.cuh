@@ -87,13 +87,9 @@ __device__ __forceinline__ void edge_setup(float e_a, float e_b, bool flip, floa
 	d = fadd(fadd(fmul(-1.0f, dot2(na, nb, va, vb)), max0(fmul(ua, na))), max0(fmul(ub, nb)));
 }
 
-__device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, SurfSetup& s) {
-	// :68-70 edges
-	float e0x = fsub(t.v1x, t.v0x), e0y = fsub(t.v1y, t.v0y), e0z = fsub(t.v1z, t.v0z);
-	float e1x = fsub(t.v2x, t.v1x), e1y = fsub(t.v2y, t.v1y), e1z = fsub(t.v2z, t.v1z);
-	float e2x = fsub(t.v0x, t.v2x), e2y = fsub(t.v0y, t.v2y), e2z = fsub(t.v0z, t.v2z);
-	tri_normal(e0x, e0y, e0z, e1x, e1y, e1z, s.nx, s.ny, s.nz);
-	// :76-80 grid bbox = clamp(int(world / unit))
+// :76-80 grid bbox = clamp(int(world / unit)).  Independent of everything else in the setup, so callers
+// compute it first and drop triangles outside their region before paying for the rest.
+__device__ __forceinline__ void surf_bbox(const Tri& t, const GridParams& g, SurfSetup& s) {
 	const int gmax = g.G - 1;
 	s.x0 = clampi(__float2int_rz(fdiv(hmin(t.v0x, hmin(t.v1x, t.v2x)), g.ux)), 0, gmax);
 	s.y0 = clampi(__float2int_rz(fdiv(hmin(t.v0y, hmin(t.v1y, t.v2y)), g.uy)), 0, gmax);
@@ -101,6 +97,15 @@ __device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, Su
 	s.x1 = clampi(__float2int_rz(fdiv(hmax(t.v0x, hmax(t.v1x, t.v2x)), g.ux)), 0, gmax);
 	s.y1 = clampi(__float2int_rz(fdiv(hmax(t.v0y, hmax(t.v1y, t.v2y)), g.uy)), 0, gmax);
 	s.z1 = clampi(__float2int_rz(fdiv(hmax(t.v0z, hmax(t.v1z, t.v2z)), g.uz)), 0, gmax);
+}
+
+// Everything but the bbox: normal, plane offsets, the 9 edge functions.
+__device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams& g, SurfSetup& s) {
+	// :68-70 edges
+	float e0x = fsub(t.v1x, t.v0x), e0y = fsub(t.v1y, t.v0y), e0z = fsub(t.v1z, t.v0z);
+	float e1x = fsub(t.v2x, t.v1x), e1y = fsub(t.v2y, t.v1y), e1z = fsub(t.v2z, t.v1z);
+	float e2x = fsub(t.v0x, t.v2x), e2y = fsub(t.v0y, t.v2y), e2z = fsub(t.v0z, t.v2z);
+	tri_normal(e0x, e0y, e0z, e1x, e1y, e1z, s.nx, s.ny, s.nz);
 	// :83-87 plane offsets
 	float cx = (s.nx > 0.0f) ? g.ux : 0.0f;
 	float cy = (s.ny > 0.0f) ? g.uy : 0.0f;
@@ -121,6 +126,11 @@ __device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, Su
 	edge_setup(e0x, e0z, fy, t.v0z, t.v0x, g.ux, g.uz, s.zx_a[0], s.zx_b[0], s.zx_d[0]);
 	edge_setup(e1x, e1z, fy, t.v1z, t.v1x, g.ux, g.uz, s.zx_a[1], s.zx_b[1], s.zx_d[1]);
 	edge_setup(e2x, e2z, fy, t.v2z, t.v2x, g.ux, g.uz, s.zx_a[2], s.zx_b[2], s.zx_d[2]);
+}
+
+__device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, SurfSetup& s) {
+	surf_bbox(t, g, s);
+	surf_setup_tests(t, g, s);
 }
 
 // Per-(y,z)-row values of the test (cpu_voxelizer.cpp:138-159 with the x-independent products

@@ -61,6 +61,7 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris
 cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tris, cudaStream_t st);
 cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t n_verts,
                                   bool soa4, float* d_out, cudaStream_t st);
+cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st);
 cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);
 
 }  // namespace voxb

@@ -112,6 +112,17 @@ int voxb200_upload_soup(const float* host_tris9, size_t n_triangles, int soa4, f
 int voxb200_upload_indexed(const float* host_verts, size_t n_verts, const int32_t* host_faces, size_t n_faces,
                            int soa4, float** d_tris, float mesh_min[3], float mesh_max[3], void* stream);
 
+/*
+ * Multi-GPU routing (new with the z-slab sharding; the reference is single-GPU): from a device soup, keep the
+ * triangles that can touch `region` — surface: clamped grid bbox overlap (voxelize.cu:86-87); with
+ * VOXB200_SOLID: centre-sample (y,z) range overlap (voxelize_solid.cu:112-113) — into a new compact device soup
+ * (*d_routed, voxb200_free it).  Triangle order is not preserved (the table does not depend on it).
+ * Synchronises `stream` to return the count.  Voxelizing the routed soup over `region` gives the same table
+ * bytes as voxelizing the full soup over `region`.
+ */
+int voxb200_route_triangles(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* region,
+                            float** d_routed, size_t* n_routed, void* stream);
+
 /* ---- the hot path --------------------------------------------------------------------------- */
 /*
  * d_tris and d_table are device-accessible pointers (cudaMalloc or cudaMallocManaged).  `stream`

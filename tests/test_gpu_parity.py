@@ -141,6 +141,29 @@ def test_uneven_z_slabs(vb):
         assert torch.equal(torch.cat(parts), full)
 
 
+@pytest.mark.parametrize("solid", [0, 1])
+@pytest.mark.parametrize("name,g", [("bunny", 128), ("icosphere:64:128", 256)])
+def test_routed_triangles_give_same_region(vb, name, g, solid):
+    """voxb200_route_triangles: the soup routed to a slab voxelizes to the same slab bytes as the full soup, and
+    the routed counts show only boundary triangles are duplicated."""
+    import copy
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    total = 0
+    for p in range(4):
+        region, _ = vb.partition(g, False, p, 4)
+        want = fn(grid, d_tris, region=region).clone()
+        buf, n = vb.route_triangles(grid, d_tris, region, solid=bool(solid))
+        total += n
+        g2 = copy.copy(grid)
+        g2.n_triangles = n
+        got = fn(g2, buf, region=region)
+        assert torch.equal(got, want)
+        buf.close()
+    assert total >= (len(f) if not solid else 1) and total <= 2 * len(f)
+
+
 def test_upload_paths(vb):
     """Triangle upload (main.cpp:61-80 replaced): soup and indexed uploads, AoS and SoA4, plus the
     device bbox reduction, all lead to the same table as torch-owned memory."""
