@@ -1,0 +1,174 @@
+// cli_main.cpp — `cuda_voxelizer`: the reference's command-line surface (src/main.cpp:109-155 flags
+// -f -s -o -cpu -solid -h, same defaults, same log sections) driving the B200 path through the C ABI.
+//   -cpu is accepted but refused: this product has no CPU voxelizer (the reference's lives in oracle/ as a checker).
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/voxb200.h"
+#include "cli.h"
+
+using namespace voxcli;
+
+namespace {
+enum class Format { binvox, morton, obj_points, obj_cubes, vox };
+const char* kFormatNames[] = {"binvox file", "morton encoded blob", "obj file (pointcloud)", "obj file (cubes)", "magicavoxel file"};
+
+struct Options {
+	std::string filename;
+	unsigned int gridsize = 256;
+	Format format = Format::vox;
+	bool force_cpu = false;
+	bool solid = false;
+};
+
+void print_help() {
+	printf("\n## HELP  \n");
+	printf("Program options: \n\n");
+	printf(" -f <path to model file: .ply, .obj> (required)\n");
+	printf(" -s <voxelization grid size, power of 2: 8 -> 512, 1024, ... (default: 256)>\n");
+	printf(" -o <output format: vox, binvox, obj, obj_points or morton (default: vox)>\n");
+	printf(" -cpu : (reference flag) not available: this build voxelizes on a B200 only\n");
+	printf(" -solid : Force solid voxelization (experimental, needs watertight model)\n\n");
+	printf("Example: cuda_voxelizer -f /home/jeroen/bunny.ply -s 512\n\n");
+}
+
+Options parse(int argc, char* argv[]) {
+	Options o;
+	if (argc < 2) { printf("Not enough program parameters. \n \n"); print_help(); exit(0); }
+	bool have_file = false;
+	for (int i = 1; i < argc; i++) {
+		const std::string a = argv[i];
+		if (a == "-f" && i + 1 < argc) {
+			o.filename = argv[++i];
+			have_file = true;
+			FILE* probe = fopen(o.filename.c_str(), "rb");
+			if (!probe) { printf("[Err] File does not exist / cannot access: %s \n", o.filename.c_str()); exit(1); }
+			fclose(probe);
+		} else if (a == "-s" && i + 1 < argc) {
+			o.gridsize = (unsigned int)atoi(argv[++i]);
+		} else if (a == "-h") {
+			print_help(); exit(0);
+		} else if (a == "-o" && i + 1 < argc) {
+			std::string f = argv[++i];
+			std::transform(f.begin(), f.end(), f.begin(), ::tolower);
+			if (f == "binvox") o.format = Format::binvox;
+			else if (f == "morton") o.format = Format::morton;
+			else if (f == "obj") o.format = Format::obj_cubes;
+			else if (f == "obj_points") o.format = Format::obj_points;
+			else if (f == "vox") o.format = Format::vox;
+			else { printf("[Err] Unrecognized output format: %s, valid options are binvox (default), morton, obj or obj_points \n", f.c_str()); exit(1); }
+		} else if (a == "-cpu") {
+			o.force_cpu = true;
+		} else if (a == "-solid") {
+			o.solid = true;
+		}
+	}
+	if (!have_file) { printf("[Err] You didn't specify a file using -f (path). This is required. Exiting. \n"); exit(1); }
+	printf("[Info] Filename: %s \n", o.filename.c_str());
+	printf("[Info] Grid size: %i \n", o.gridsize);
+	printf("[Info] Output format: %s \n", kFormatNames[(int)o.format]);
+	printf("[Info] Using CPU-based voxelization: %s (default: No)\n", o.force_cpu ? "Yes" : "No");
+	printf("[Info] Using Solid Voxelization: %s (default: No)\n", o.solid ? "Yes" : "No");
+	return o;
+}
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+[[noreturn]] void die_abi(const char* where, int rc) {
+	fprintf(stderr, "CUDA error at %s code=%d \"%s\" \n", where, rc, voxb200_last_error());
+	exit(EXIT_FAILURE);
+}
+}  // namespace
+
+int main(int argc, char* argv[]) {
+	const double t_start = now_ms();
+	printf("## CUDA VOXELIZER \n");
+	printf("CUDA Voxelizer (B200-native build, %s), drop-in for cuda_voxelizer v0.6\n", voxb200_version());
+	printf("\n## PROGRAM PARAMETERS \n");
+	const Options opt = parse(argc, argv);
+	fflush(stdout);
+
+	printf("\n## READ MESH \n");
+	printf("[I/O] Reading mesh from %s \n", opt.filename.c_str());
+	Mesh mesh;
+	std::string err;
+	if (!load_mesh(opt.filename, mesh, err)) { printf("[Err] %s \n", err.c_str()); return 1; }
+	printf("[Mesh] Number of triangles: %zu \n", mesh.n_faces());
+	printf("[Mesh] Number of vertices: %zu \n", mesh.n_vertices());
+	printf("[Mesh] Computing bbox \n");
+
+	printf("\n## VOXELISATION SETUP \n");
+	voxb200_grid grid;
+	int rc = voxb200_make_grid(mesh.bbox_min, mesh.bbox_max, opt.gridsize, mesh.n_faces(), &grid);
+	if (rc) die_abi("voxb200_make_grid", rc);
+	const voxinfo& info = *reinterpret_cast<const voxinfo*>(&grid);
+	printf("[Voxelization] Bounding Box: (%f,%f,%f)-(%f,%f,%f) \n", info.bbox.min.x, info.bbox.min.y, info.bbox.min.z, info.bbox.max.x, info.bbox.max.y, info.bbox.max.z);
+	printf("[Voxelization] Grid size: %i %i %i \n", info.gridsize.x, info.gridsize.y, info.gridsize.z);
+	printf("[Voxelization] Triangles: %zu \n", info.n_triangles);
+	printf("[Voxelization] Unit length: x: %f y: %f z: %f\n", info.unit.x, info.unit.y, info.unit.z);
+	const size_t vtable_size = voxb200_table_bytes(opt.gridsize);
+
+	if (opt.force_cpu) {
+		printf("\n## CPU VOXELISATION \n");
+		printf("[Err] -cpu: this build has no CPU voxelization path (it targets B200 GPUs only; the reference's CPU voxelizer is kept as a test oracle, not as a product path). Run without -cpu. \n");
+		return 1;
+	}
+	printf("\n## CUDA INIT \n");
+	if (!initCuda()) {
+		printf("[Err] No usable CUDA GPU was found and this build has no CPU fallback. \n");
+		return 1;
+	}
+
+	printf("\n## TRIANGLES TO GPU TRANSFER \n");
+	const double t_up = now_ms();
+	float* d_tris = nullptr;
+	printf("[Mesh] Uploading %zu vertices + %zu faces; expanding to %zu bytes of triangle data on the GPU \n", mesh.n_vertices(), mesh.n_faces(), mesh.n_faces() * 36);
+	rc = voxb200_upload_indexed(mesh.vertices.data(), mesh.n_vertices(), mesh.faces.data(), mesh.n_faces(), 0, &d_tris, nullptr, nullptr, nullptr);
+	if (rc) die_abi("voxb200_upload_indexed", rc);
+	printf("[Perf] Mesh transfer time to GPU: %.1f ms \n", now_ms() - t_up);
+
+	printf("[Voxel Grid] Allocating %zu bytes of device memory for Voxel Grid\n", vtable_size);
+	unsigned int* d_table = nullptr;
+	rc = voxb200_malloc(reinterpret_cast<void**>(&d_table), vtable_size);
+	if (rc) die_abi("voxb200_malloc", rc);
+
+	printf("\n## GPU VOXELISATION \n");
+	const bool morton = opt.format == Format::morton;
+	cudaEvent_t e0, e1;
+	cudaEventCreate(&e0); cudaEventCreate(&e1);
+	cudaEventRecord(e0, 0);
+	const unsigned int flags = morton ? VOXB200_MORTON : 0u;       // clears the table itself (cudaMalloc memory is not zero)
+	rc = opt.solid ? voxb200_solid(&grid, d_tris, d_table, flags, nullptr, nullptr) : voxb200_surface(&grid, d_tris, d_table, flags, nullptr, nullptr);
+	if (rc) die_abi(opt.solid ? "voxb200_solid" : "voxb200_surface", rc);
+	cudaEventRecord(e1, 0);
+	if (cudaDeviceSynchronize() != cudaSuccess) { fprintf(stderr, "CUDA error at voxelization: %s \n", cudaGetErrorString(cudaGetLastError())); return EXIT_FAILURE; }
+	float ms = 0.0f;
+	cudaEventElapsedTime(&ms, e0, e1);
+	printf("[Perf] Voxelization GPU time: %.1f ms\n", ms);
+
+	std::vector<unsigned int> vtable(vtable_size / 4);
+	rc = voxb200_memcpy_d2h(vtable.data(), d_table, vtable_size, nullptr);
+	if (rc) die_abi("voxb200_memcpy_d2h", rc);
+	voxb200_free(d_tris);
+	voxb200_free(d_table);
+
+	printf("\n## FILE OUTPUT \n");
+	switch (opt.format) {
+		case Format::morton: write_binary(vtable.data(), vtable_size, opt.filename); break;
+		case Format::binvox: write_binvox(vtable.data(), info, opt.filename); break;
+		case Format::obj_points: write_obj_pointcloud(vtable.data(), info, opt.filename); break;
+		case Format::obj_cubes: write_obj_cubes(vtable.data(), info, opt.filename); break;
+		case Format::vox: write_vox(vtable.data(), info, opt.filename); break;
+	}
+	printf("\n## STATS \n");
+	printf("[Perf] Total runtime: %.1f ms \n", now_ms() - t_start);
+	return 0;
+}

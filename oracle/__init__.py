@@ -190,3 +190,24 @@ def ref_voxelize(verts, faces, gridsize, solid=False, morton=False, threads=None
 
 def ref_max_threads():
     return int(ref().voxref_max_threads())
+
+
+# ----------------------------------------------------------------------------- compiled reference writers
+_REF_IO_SO = os.path.join(_HERE, "_ref", "libvoxref_io.so")
+_ref_io = None
+
+
+def have_ref_io():
+    return os.path.exists(_REF_IO_SO)
+
+
+def ref_write(fmt, table, gridsize, bbox_min, bbox_max, n_tris, base_filename):
+    """Run one of the reference's own writers (util_io.cpp): fmt in binvox|morton|obj_points|obj|vox."""
+    global _ref_io
+    if _ref_io is None:
+        _ref_io = C.CDLL(_REF_IO_SO)
+        _ref_io.voxref_write.argtypes = [C.c_int, _u32p, C.c_uint, _f32p, _f32p, C.c_size_t, C.c_char_p]
+    code = {"binvox": 0, "morton": 1, "obj_points": 2, "obj": 3, "vox": 4}[fmt]
+    rc = _ref_io.voxref_write(code, np.ascontiguousarray(table, np.uint32), gridsize, np.ascontiguousarray(bbox_min, np.float32),
+                              np.ascontiguousarray(bbox_max, np.float32), n_tris, base_filename.encode())
+    assert rc == 0

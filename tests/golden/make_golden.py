@@ -61,6 +61,33 @@ def main():
     if small_tables:
         np.savez_compressed(os.path.join(HERE, "tables_small.npz"), **small_tables)
     print("voxinfo layout:", oracle.ref_voxinfo_layout())
+    make_writer_goldens(verts, faces)
+
+
+def make_writer_goldens(verts, faces):
+    """Golden OUTPUT FILES from the reference's own writers (util_io.cpp), bunny surface @32 (morton table for -o morton)."""
+    import shutil
+    import tempfile
+    g = 32
+    out_dir = os.path.join(HERE, "io")
+    os.makedirs(out_dir, exist_ok=True)
+    mn, mx, unit = oracle.ref_voxinfo(verts, g, len(faces))
+    lin = oracle.ref_voxelize(verts, faces, g, threads=1)
+    mor = oracle.ref_voxelize(verts, faces, g, morton=True, threads=1)
+    tmp = tempfile.mkdtemp()
+    base = os.path.join(tmp, "bunny.OBJ")
+    index = {}
+    for fmt, table, produced in (("binvox", lin, "bunny.OBJ_%d.binvox" % g), ("morton", mor, "bunny.OBJ.bin"),
+                                 ("obj_points", lin, "bunny.OBJ_%d_pointcloud.obj" % g), ("obj", lin, "bunny.OBJ_%d_voxels.obj" % g),
+                                 ("vox", lin, "bunny.OBJ_%d.vox" % g)):
+        oracle.ref_write(fmt, table, g, mn, mx, len(faces), base)
+        data = open(os.path.join(tmp, produced), "rb").read()
+        index[fmt] = {"file": produced, "bytes": len(data), "fnv1a64": "%016x" % oracle.fnv1a64(np.frombuffer(data, np.uint8))}
+        if fmt in ("binvox", "vox"):
+            shutil.copy(os.path.join(tmp, produced), os.path.join(out_dir, produced))
+        print("writer golden %-10s %-32s %8d bytes %s" % (fmt, produced, len(data), index[fmt]["fnv1a64"]))
+    json.dump({"gridsize": g, "files": index}, open(os.path.join(out_dir, "index.json"), "w"), indent=1, sort_keys=True)
+    shutil.rmtree(tmp)
 
 
 if __name__ == "__main__":
