@@ -311,9 +311,16 @@ def run_ours(args):
     dom_ms = float(phases[dom])
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_alg = tri_bytes + slab_bytes
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per launch from the committed ncu capture
+    if os.path.exists(tpath) and world == 1:
+        try:
+            traffic = json.load(open(tpath)).get(wname, {}).get(names[dom])
+        except Exception:
+            traffic = None
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
+        "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
         "kernel_ms": round(dom_ms, 4), "algorithmic_bytes": int(alg_bytes[dom]),
         "phases_ms": {n: round(float(p), 4) for n, p in zip(names, phases)},
         "step": {"algorithmic_bytes": int(step_alg), "achieved_gbs": round(step_alg / (ms_per_step * 1e-3) / 1e9, 1),
@@ -338,7 +345,7 @@ def run_ours(args):
         "config": {"workload": w["desc"], "gridsize": G, "triangles": int(n_tris), "mode": "solid" if solid else "surface",
                    "sharding": "z-slab x%d, triangles routed to the slabs their bbox overlaps, no data-path collective" % world,
                    "l2": "inputs larger than L2 (%.0f MB soup + %.0f MB table slab per GPU vs 126 MB L2)" % (tri_bytes / 1e6, slab_bytes / 1e6)},
-        "e2e": {"value": round(n_tris / e2e_ms / 1e3, 2), "unit": "Mtri/s", "h2d_bytes_per_step": int(tri_bytes), "d2h_bytes_per_step": int(slab_bytes),
+        "e2e": {"value": round(n_tris / e2e_ms / 1e3, 2), "unit": "Mtri/s", "h2d_bytes_per_step": int(36 * n_tris), "d2h_bytes_per_step": int(slab_bytes),
                 "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall, 3), "steps": e2e_steps,
                 "api": "voxb200_voxelize_host (pinned host soup -> H2D -> voxelize -> D2H table slab), per rank"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
