@@ -78,7 +78,7 @@ __device__ __forceinline__ bool clip_to_region(const GridParams& g, SurfSetup& s
 //   * a test's outcome is the SIGN BIT of its value, shifted into a reject mask with one funnel shift:
 //       edge test  "v < 0"          -> sign(min(v_e0, v_e1, v_e2))   (v is never -0: its last addend d_e never is)
 //       plane test "(s+d1)(s+d2) > 0" -> sign(0 - P)                 (0 - P is -0 for no P; NaN is canonical, sign clear)
-//   * voxel b = i + 3j + 9k survives iff it is inside the bbox and none of the four masks rejects it.
+//   * voxel b = (2-i) + 3j + 9k (x0 at the high bit of each 3-bit row, MSB-first like the table) survives iff it is inside the bbox and none of the four masks rejects it.
 // Survivors are written one (y,z) row at a time: the 3 x-bits of a row go out as one or two atomicOr.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {       // mask = (mask << 1) | signbit(v)
@@ -103,7 +103,7 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 #pragma unroll
 		for (int j = 2; j >= 0; j--)
 #pragma unroll
-			for (int i = 2; i >= 0; i--) {
+			for (int i = 0; i < 3; i++) {               // x ascending: x0 ends up at the HIGH bit of its row (MSB-first, like the table)
 				const float sdp = fadd(fadd(nxp[i], nyp[j]), nzp[k]);
 				const float prod = fmul(fadd(sdp, s.d1), fadd(sdp, s.d2));
 				rej = sign_in(rej, fsub(0.0f, prod));
@@ -119,7 +119,7 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 #pragma unroll
 		for (int j = 2; j >= 0; j--)
 #pragma unroll
-			for (int i = 2; i >= 0; i--) {
+			for (int i = 0; i < 3; i++) {
 				const float v0 = fadd(fadd(a[0][i], b[0][j]), s.xy_d[0]);
 				const float v1 = fadd(fadd(a[1][i], b[1][j]), s.xy_d[1]);
 				const float v2 = fadd(fadd(a[2][i], b[2][j]), s.xy_d[2]);
@@ -153,14 +153,14 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 #pragma unroll
 		for (int k = 2; k >= 0; k--)
 #pragma unroll
-			for (int i = 2; i >= 0; i--) {
+			for (int i = 0; i < 3; i++) {
 				const float v0 = fadd(fadd(a[0][k], b[0][i]), s.zx_d[0]);
 				const float v1 = fadd(fadd(a[1][k], b[1][i]), s.zx_d[1]);
 				const float v2 = fadd(fadd(a[2][k], b[2][i]), s.zx_d[2]);
 				rzx = sign_in(rzx, fminf(fminf(v0, v1), v2));
 			}
 	}
-	// expand the 9-bit cell masks to the 27-bit voxel layout b = i + 3j + 9k
+	// expand the 9-bit cell masks to the 27-bit voxel layout b = (2-i) + 3j + 9k
 	const unsigned int xy27 = rxy * 0x40201u;                                           // copies at +0, +9, +18
 	const unsigned int yz_s = (ryz & 0x1u) | ((ryz & 0x2u) << 2) | ((ryz & 0x4u) << 4) | ((ryz & 0x8u) << 6) | ((ryz & 0x10u) << 8) |
 	                          ((ryz & 0x20u) << 10) | ((ryz & 0x40u) << 12) | ((ryz & 0x80u) << 14) | ((ryz & 0x100u) << 16);   // bit (j+3k) -> 3j+9k
@@ -168,11 +168,11 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 	const unsigned int zx_s = (rzx & 0x7u) | ((rzx & 0x38u) << 6) | ((rzx & 0x1c0u) << 12);                                     // bit (i+3k) -> i+9k
 	const unsigned int zx27 = zx_s * 0x49u;                                             // copies at +0, +3, +6
 	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..2
-	const unsigned int valid = (((2u << ex) - 1u) * 0x1249249u) & (((8u << (3 * ey)) - 1u) * 0x40201u) & ((512u << (9 * ez)) - 1u);
+	const unsigned int valid = (((7u << (2 - ex)) & 7u) * 0x1249249u) & (((8u << (3 * ey)) - 1u) * 0x40201u) & ((512u << (9 * ez)) - 1u);
 	return valid & ~(rej | xy27 | yz27 | zx27);
 }
 
-// Writes a 27-bit hit mask (bit i + 3j + 9k = voxel (x0+i, y0+j, z0+k)) into the table: one (y,z) row — three
+// Writes a 27-bit hit mask (bit (2-i) + 3j + 9k = voxel (x0+i, y0+j, z0+k)) into the table: one (y,z) row — three
 // x-adjacent bits — at a time, as one atomicOr, or two when the row straddles a word.
 template <bool MORTON>
 __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, int z0, const GridParams& g,
@@ -183,7 +183,7 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 		while (hit) {
 			const int b = __ffs(hit) - 1;
 			hit &= hit - 1u;
-			const int k = b / 9, j = (b - 9 * k) / 3, i = b - 9 * k - 3 * j;
+			const int k = b / 9, j = (b - 9 * k) / 3, i = 2 - (b - 9 * k - 3 * j);
 			const unsigned long long idx = morton3((unsigned)(x0 + i), (unsigned)(y0 + j), (unsigned)(z0 + k));
 			const unsigned long long w = (idx >> 5) - g.word_base;
 			if (w != cur) { if (mask) atomicOr(table + cur, mask); cur = w; mask = 0u; }
@@ -199,11 +199,11 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 		const unsigned int sh = (unsigned int)x0 & 31u;
 		while (hit) {
 			const int r = (__ffs(hit) - 1) / 3;                    // row = j + 3k
-			const unsigned int bits = (hit >> (3 * r)) & 7u;        // x0, x0+1, x0+2
+			const unsigned int bits = (hit >> (3 * r)) & 7u;        // x0 at bit 2 ... x0+2 at bit 0
 			hit &= ~(7u << (3 * r));
 			const int k = r / 3, j = r - 3 * k;
 			const unsigned int w = w0 + Gw * ((unsigned int)j + (unsigned int)g.G * (unsigned int)k);
-			const unsigned int v = __brev(bits);                    // x0 -> bit 31, x0+1 -> 30, x0+2 -> 29
+			const unsigned int v = bits << 29;                      // x0 -> bit 31, x0+1 -> 30, x0+2 -> 29
 			const unsigned int hi = v >> sh, lo = __funnelshift_r(0u, v, sh);
 			if (hi) atomicOr(table + w, hi);
 			if (lo) atomicOr(table + w + 1, lo);
@@ -218,7 +218,7 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 		const int k = r / 3, j = r - 3 * k;
 		const unsigned long long idx = (unsigned long long)x0 + G * ((unsigned long long)(y0 + j) + G * (unsigned long long)(z0 + k));
 		// voxel idx+t sits at bit 31-((idx+t)&31): put the row MSB-first into a 64-bit window over words w, w+1
-		const unsigned long long win = ((unsigned long long)(__brev(bits) >> 29) << 61) >> (unsigned int)(idx & 31ull);
+		const unsigned long long win = ((unsigned long long)bits << 61) >> (unsigned int)(idx & 31ull);
 		const unsigned long long w = (idx >> 5) - g.word_base;
 		const unsigned int hi = (unsigned int)(win >> 32), lo = (unsigned int)win;
 		if (hi) atomicOr(table + w, hi);

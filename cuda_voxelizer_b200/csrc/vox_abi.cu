@@ -87,6 +87,7 @@ int resolve_region(const voxb200_grid* grid, const voxb200_region* region, bool 
 	const unsigned long long G3 = (unsigned long long)G * G * G;
 	g->bx = grid->bbox_min[0]; g->by = grid->bbox_min[1]; g->bz = grid->bbox_min[2];
 	g->ux = grid->unit[0]; g->uy = grid->unit[1]; g->uz = grid->unit[2];
+	g->rux = 1.0f / g->ux; g->ruy = 1.0f / g->uy; g->ruz = 1.0f / g->uz;
 	g->G = (int)G;
 	g->n_tris = grid->n_triangles;
 	if (grid->n_triangles > 0xfffffff0ull) return fail(VOXB200_EINVAL, "more than 2^32 triangles in one call");

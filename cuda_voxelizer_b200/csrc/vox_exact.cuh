@@ -20,6 +20,7 @@ namespace voxb {
 struct GridParams {
 	float bx, by, bz;          // bbox.min
 	float ux, uy, uz;          // unit
+	float rux, ruy, ruz;       // fl(1 / unit): fast path of grid_coord() only, never part of a result
 	int G;                     // gridsize (cubic, main.cpp:186)
 	int rx0, rx1;              // region [lo, hi) per axis (z-slab, or morton octant)
 	int ry0, ry1;
@@ -35,7 +36,8 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 // host fallbacks of helper_math.h:58-66 (a<b?a:b), and std::max(0.0f,x) (§A-8)
 __device__ __forceinline__ float hmin(float a, float b) { return a < b ? a : b; }
 __device__ __forceinline__ float hmax(float a, float b) { return a > b ? a : b; }
-__device__ __forceinline__ float max0(float x) { return (0.0f < x) ? x : 0.0f; }
+// std::max(0.0f, x) = (0 < x) ? x : 0: equals fmaxf(x, +0) for EVERY input (NaN -> 0, -0 -> +0, x <= 0 -> +0), one FMNMX
+__device__ __forceinline__ float max0(float x) { return fmaxf(x, 0.0f); }
 __device__ __forceinline__ float dot2(float ax, float ay, float bx, float by) {       // helper_math.h:1260
 	return fadd(fmul(ax, bx), fmul(ay, by));
 }
@@ -89,14 +91,30 @@ __device__ __forceinline__ void edge_setup(float e_a, float e_b, bool flip, floa
 
 // :76-80 grid bbox = clamp(int(world / unit)).  Independent of everything else in the setup, so callers
 // compute it first and drop triangles outside their region before paying for the rest.
+// trunc(fl(v / u)) — the reference's float3_to_int3(world / unit) — without the IEEE division whenever the answer
+// is unambiguous.  q = fl(v * fl(1/u)) differs from the correctly rounded quotient Q = fl(v/u) by less than
+// |q| * 2^-22 (two roundings in q, one in Q).  If q is further than |q| * 2^-21 from both neighbouring integers then
+// q and Q lie strictly inside the same (t, t+1) and truncate alike; otherwise (about one coordinate in 10^3) the
+// real division decides.  Negative, huge and NaN quotients take the division too.
+__device__ __forceinline__ int grid_coord(float v, float u, float ru) {
+	const float q = fmul(v, ru);
+	const int t = __float2int_rz(q);
+	const float f = fsub(q, (float)t);
+	const float tol = fmul(q, 4.76837158203125e-07f);        // |q| * 2^-21 (q > 0 on this path)
+	if (q > 0.0f && q < 1.0e6f && f > tol && fsub(1.0f, f) > tol) return t;
+	return __float2int_rz(fdiv(v, u));
+}
+
 __device__ __forceinline__ void surf_bbox(const Tri& t, const GridParams& g, SurfSetup& s) {
 	const int gmax = g.G - 1;
-	s.x0 = clampi(__float2int_rz(fdiv(hmin(t.v0x, hmin(t.v1x, t.v2x)), g.ux)), 0, gmax);
-	s.y0 = clampi(__float2int_rz(fdiv(hmin(t.v0y, hmin(t.v1y, t.v2y)), g.uy)), 0, gmax);
-	s.z0 = clampi(__float2int_rz(fdiv(hmin(t.v0z, hmin(t.v1z, t.v2z)), g.uz)), 0, gmax);
-	s.x1 = clampi(__float2int_rz(fdiv(hmax(t.v0x, hmax(t.v1x, t.v2x)), g.ux)), 0, gmax);
-	s.y1 = clampi(__float2int_rz(fdiv(hmax(t.v0y, hmax(t.v1y, t.v2y)), g.uy)), 0, gmax);
-	s.z1 = clampi(__float2int_rz(fdiv(hmax(t.v0z, hmax(t.v1z, t.v2z)), g.uz)), 0, gmax);
+	// min/max: the host fallbacks a<b?a:b / a>b?a:b (helper_math.h:58-66) equal FMNMX for all non-NaN inputs up to the
+	// sign of a zero, which the int conversion below discards
+	s.x0 = clampi(grid_coord(fminf(t.v0x, fminf(t.v1x, t.v2x)), g.ux, g.rux), 0, gmax);
+	s.y0 = clampi(grid_coord(fminf(t.v0y, fminf(t.v1y, t.v2y)), g.uy, g.ruy), 0, gmax);
+	s.z0 = clampi(grid_coord(fminf(t.v0z, fminf(t.v1z, t.v2z)), g.uz, g.ruz), 0, gmax);
+	s.x1 = clampi(grid_coord(fmaxf(t.v0x, fmaxf(t.v1x, t.v2x)), g.ux, g.rux), 0, gmax);
+	s.y1 = clampi(grid_coord(fmaxf(t.v0y, fmaxf(t.v1y, t.v2y)), g.uy, g.ruy), 0, gmax);
+	s.z1 = clampi(grid_coord(fmaxf(t.v0z, fmaxf(t.v1z, t.v2z)), g.uz, g.ruz), 0, gmax);
 }
 
 // Everything but the bbox: normal, plane offsets, the 9 edge functions.
