@@ -236,7 +236,7 @@ template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
                                                                 unsigned int* __restrict__ table,
                                                                 unsigned long long* __restrict__ counters,
-                                                                uint2* __restrict__ queue) {
+                                                                uint2* __restrict__ queue, uint4* __restrict__ setups, unsigned int setup_cap) {
 	__shared__ __align__(16) float stage[SOA4 ? 4 : (kTriBlock / 32) * 288];
 	const int lane = threadIdx.x & 31;
 	const unsigned long long tile = ((unsigned long long)blockIdx.x * kTriBlock + threadIdx.x) >> 5;
@@ -282,7 +282,8 @@ __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams
 			items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
 		}
 	}
-	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
+	const unsigned int slot = enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
+	if (slot < setup_cap) store_setup(setups + (size_t)slot * kSetupVec, s);
 	if (!live || big) return;
 	const unsigned int hit = surf_micro3(s, g);
 	if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
@@ -311,13 +312,36 @@ template <typename Pred>
 __device__ __forceinline__ int last_true(int lo, int hi, Pred pred) {
 	return first_true(lo, hi, [&](int x) { return !pred(x); }) - 1;
 }
+// The same two searches, started from an estimate `e` of the answer (the real-arithmetic root of the test, computed
+// with a fast reciprocal).  The estimate only chooses WHERE the exact predicate is evaluated first: two evaluations
+// confirm it when it is right (the common case), otherwise bisection finishes on the side the evaluations point to.
+template <typename Pred>
+__device__ __forceinline__ int first_true_from(int lo, int hi, int e, Pred pred) {
+	e = max(lo, min(e, hi));
+	if (pred(e)) {
+		if (e == lo || !pred(e - 1)) return e;
+		return first_true(lo, e - 1, pred);
+	}
+	if (e == hi) return hi + 1;
+	if (pred(e + 1)) return e + 1;
+	return first_true(e + 2, hi, pred);
+}
+template <typename Pred>
+__device__ __forceinline__ int last_true_from(int lo, int hi, int e, Pred pred) {
+	return first_true_from(lo, hi, e + 1, [&](int x) { return !pred(x); }) - 1;
+}
+// float -> int for estimates: saturating, NaN -> 0 (any value is acceptable, the predicate decides)
+__device__ __forceinline__ int est_ceil(float v) { return __float2int_ru(v); }
+__device__ __forceinline__ int est_floor(float v) { return __float2int_rd(v); }
+
 // Narrow [lo, hi] to the x accepted by `acc`, which is monotone in x with direction sign(coef):
 // coef > 0: rejected...accepted; coef < 0: accepted...rejected; otherwise constant in x.
+// `root` estimates the x where the test value crosses zero.
 template <typename Acc>
-__device__ __forceinline__ void narrow(int& lo, int& hi, float coef, Acc acc) {
+__device__ __forceinline__ void narrow(int& lo, int& hi, float coef, float root, Acc acc) {
 	if (lo > hi) return;
-	if (coef > 0.0f) lo = first_true(lo, hi, acc);
-	else if (coef < 0.0f) hi = last_true(lo, hi, acc);
+	if (coef > 0.0f) lo = first_true_from(lo, hi, est_ceil(root), acc);
+	else if (coef < 0.0f) hi = last_true_from(lo, hi, est_floor(root), acc);
 	else if (!acc(lo)) hi = lo - 1;
 }
 
@@ -334,29 +358,39 @@ __device__ __forceinline__ void surf_solve_row(const SurfSetup& s, const GridPar
 		below = a < 0.0f;
 		return fmul(a, fadd(ndp, s.d2)) > 0.0f;       // true = rejected
 	};
-	if (s.nx > 0.0f) {
-		lo = first_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && b); });
-		if (lo <= hi) hi = last_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && !b); });
-	} else if (s.nx < 0.0f) {
-		lo = first_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && !b); });
-		if (lo <= hi) hi = last_true(lo, hi, [&](int x) { bool b; return !(plane(x, b) && b); });
+	if (s.nx > 0.0f || s.nx < 0.0f) {
+		// the two factors cross zero near xA and xB; the accepted voxels lie between them
+		const float inv = __fdividef(1.0f, s.nx * g.ux), c = r.ny_py + r.nz_pz;
+		const float xA = -(c + s.d1) * inv, xB = -(c + s.d2) * inv;
+		const int e_lo = est_ceil(fminf(xA, xB)), e_hi = est_floor(fmaxf(xA, xB));
+		if (s.nx > 0.0f) {
+			lo = first_true_from(lo, hi, e_lo, [&](int x) { bool b; return !(plane(x, b) && b); });
+			if (lo <= hi) hi = last_true_from(lo, hi, e_hi, [&](int x) { bool b; return !(plane(x, b) && !b); });
+		} else {
+			lo = first_true_from(lo, hi, e_lo, [&](int x) { bool b; return !(plane(x, b) && !b); });
+			if (lo <= hi) hi = last_true_from(lo, hi, e_hi, [&](int x) { bool b; return !(plane(x, b) && b); });
+		}
 	} else {
 		bool b;
 		if (plane(lo, b)) hi = lo - 1;                // n.x is 0 or NaN: the test does not depend on x
 	}
 #pragma unroll
-	for (int k = 0; k < 3; k++)                        // XY edges (:144-147): value moves with sign(n_xy_e.x)
-		narrow(lo, hi, s.xy_a[k], [&](int x) { return !(fadd(fadd(fmul(s.xy_a[k], fmul((float)x, g.ux)), r.xy_bpy[k]), s.xy_d[k]) < 0.0f); });
+	for (int k = 0; k < 3; k++) {                      // XY edges (:144-147): value moves with sign(n_xy_e.x)
+		const float root = __fdividef(-(r.xy_bpy[k] + s.xy_d[k]), s.xy_a[k] * g.ux);
+		narrow(lo, hi, s.xy_a[k], root, [&](int x) { return !(fadd(fadd(fmul(s.xy_a[k], fmul((float)x, g.ux)), r.xy_bpy[k]), s.xy_d[k]) < 0.0f); });
+	}
 #pragma unroll
-	for (int k = 0; k < 3; k++)                        // ZX edges (:156-159): value moves with sign(n_zx_e.y)
-		narrow(lo, hi, s.zx_b[k], [&](int x) { return !(fadd(fadd(r.zx_apz[k], fmul(s.zx_b[k], fmul((float)x, g.ux))), s.zx_d[k]) < 0.0f); });
+	for (int k = 0; k < 3; k++) {                      // ZX edges (:156-159): value moves with sign(n_zx_e.y)
+		const float root = __fdividef(-(r.zx_apz[k] + s.zx_d[k]), s.zx_b[k] * g.ux);
+		narrow(lo, hi, s.zx_b[k], root, [&](int x) { return !(fadd(fadd(r.zx_apz[k], fmul(s.zx_b[k], fmul((float)x, g.ux))), s.zx_d[k]) < 0.0f); });
+	}
 }
 
 template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g, const float* __restrict__ tris,
                                                               unsigned int* __restrict__ table,
                                                               const unsigned long long* __restrict__ counters,
-                                                              const uint2* __restrict__ queue) {
+                                                              const uint2* __restrict__ queue, const uint4* __restrict__ setups, unsigned int setup_cap) {
 	const unsigned long long packed = counters[kCtrQueue];
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_items = (unsigned int)packed;
@@ -372,12 +406,16 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 			if (__ldg(&queue[mid].y) <= item) lo_e = mid; else hi_e = mid - 1u;
 		}
 		const uint2 e = __ldg(&queue[lo_e]);
-		Tri t;
-		if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
-		shift_tri(t, g);
 		SurfSetup s;
-		surf_setup(t, g, s);
-		clip_to_region(g, s);
+		if (lo_e < setup_cap) {
+			load_setup(setups + (size_t)lo_e * kSetupVec, s);       // computed once by the per-triangle kernel
+		} else {
+			Tri t;
+			if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
+			shift_tri(t, g);
+			surf_setup(t, g, s);
+			clip_to_region(g, s);
+		}
 		const int ny = s.y1 - s.y0 + 1;
 		const long long rows = (long long)ny * (long long)(s.z1 - s.z0 + 1);
 		const long long r = (long long)(item - e.y) * kRowsPerItem + sub;
@@ -413,7 +451,7 @@ template <bool MORTON, bool SOA4>
 static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table, cudaStream_t st) {
 	const unsigned long long tiles = (g.n_tris + 31ull) / 32ull;
 	const unsigned long long blocks = (tiles + (kTriBlock / 32) - 1) / (kTriBlock / 32);
-	surface_tri_kernel<MORTON, SOA4><<<(unsigned)blocks, kTriBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
+	surface_tri_kernel<MORTON, SOA4><<<(unsigned)blocks, kTriBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue, ws.setups, (unsigned int)ws.setup_cap);
 	g_launch_count++;
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
@@ -422,7 +460,7 @@ static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* 
 	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
-	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue);
+	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue, ws.setups, (unsigned int)ws.setup_cap);
 	g_launch_count++;
 	return cudaGetLastError();
 }

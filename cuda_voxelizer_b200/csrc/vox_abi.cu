@@ -211,8 +211,17 @@ cudaError_t ensure_queue(Workspace& ws, size_t entries) {
 	ws.queue = nullptr; ws.queue_cap = 0;
 	size_t cap = entries + entries / 8 + 1024;
 	cudaError_t e = cudaMalloc(&ws.queue, cap * sizeof(uint2));
-	if (e == cudaSuccess) ws.queue_cap = cap;
-	return e;
+	if (e != cudaSuccess) return e;
+	ws.queue_cap = cap;
+	// setups of queued triangles: bounded (160 B each); queue slots beyond the cap recompute their setup instead
+	const size_t want = cap < (size_t(1) << 21) ? cap : (size_t(1) << 21);
+	if (want > ws.setup_cap) {
+		if (ws.setups) cudaFree(ws.setups);
+		ws.setups = nullptr; ws.setup_cap = 0;
+		if (cudaMalloc(&ws.setups, want * kSetupVec * sizeof(uint4)) == cudaSuccess) ws.setup_cap = want;
+		else cudaGetLastError();          // optional: without it every slot recomputes
+	}
+	return cudaSuccess;
 }
 cudaError_t ensure_scratch(Workspace& ws, size_t words) {
 	if (words <= ws.scratch_words) return cudaSuccess;

@@ -151,6 +151,39 @@ __device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, Su
 	surf_setup_tests(t, g, s);
 }
 
+// A queued triangle's setup travels from the per-triangle kernel to the cooperative kernel as 10 x 16 bytes
+// (the bbox is the region-clipped one; coordinates fit 16 bits for G <= 65536).
+constexpr int kSetupVec = 10;
+__device__ __forceinline__ void store_setup(uint4* __restrict__ dst, const SurfSetup& s) {
+#define VOXB_U(x) __float_as_uint(x)
+	dst[0] = make_uint4(VOXB_U(s.nx), VOXB_U(s.ny), VOXB_U(s.nz), VOXB_U(s.d1));
+	dst[1] = make_uint4(VOXB_U(s.d2), VOXB_U(s.xy_a[0]), VOXB_U(s.xy_a[1]), VOXB_U(s.xy_a[2]));
+	dst[2] = make_uint4(VOXB_U(s.xy_b[0]), VOXB_U(s.xy_b[1]), VOXB_U(s.xy_b[2]), VOXB_U(s.xy_d[0]));
+	dst[3] = make_uint4(VOXB_U(s.xy_d[1]), VOXB_U(s.xy_d[2]), VOXB_U(s.yz_a[0]), VOXB_U(s.yz_a[1]));
+	dst[4] = make_uint4(VOXB_U(s.yz_a[2]), VOXB_U(s.yz_b[0]), VOXB_U(s.yz_b[1]), VOXB_U(s.yz_b[2]));
+	dst[5] = make_uint4(VOXB_U(s.yz_d[0]), VOXB_U(s.yz_d[1]), VOXB_U(s.yz_d[2]), VOXB_U(s.zx_a[0]));
+	dst[6] = make_uint4(VOXB_U(s.zx_a[1]), VOXB_U(s.zx_a[2]), VOXB_U(s.zx_b[0]), VOXB_U(s.zx_b[1]));
+	dst[7] = make_uint4(VOXB_U(s.zx_b[2]), VOXB_U(s.zx_d[0]), VOXB_U(s.zx_d[1]), VOXB_U(s.zx_d[2]));
+	dst[8] = make_uint4((unsigned)s.x0 | ((unsigned)s.x1 << 16), (unsigned)s.y0 | ((unsigned)s.y1 << 16), (unsigned)s.z0 | ((unsigned)s.z1 << 16), 0u);
+	dst[9] = make_uint4(0u, 0u, 0u, 0u);
+#undef VOXB_U
+}
+__device__ __forceinline__ void load_setup(const uint4* __restrict__ src, SurfSetup& s) {
+#define VOXB_F(x) __uint_as_float(x)
+	uint4 v;
+	v = __ldg(src + 0); s.nx = VOXB_F(v.x); s.ny = VOXB_F(v.y); s.nz = VOXB_F(v.z); s.d1 = VOXB_F(v.w);
+	v = __ldg(src + 1); s.d2 = VOXB_F(v.x); s.xy_a[0] = VOXB_F(v.y); s.xy_a[1] = VOXB_F(v.z); s.xy_a[2] = VOXB_F(v.w);
+	v = __ldg(src + 2); s.xy_b[0] = VOXB_F(v.x); s.xy_b[1] = VOXB_F(v.y); s.xy_b[2] = VOXB_F(v.z); s.xy_d[0] = VOXB_F(v.w);
+	v = __ldg(src + 3); s.xy_d[1] = VOXB_F(v.x); s.xy_d[2] = VOXB_F(v.y); s.yz_a[0] = VOXB_F(v.z); s.yz_a[1] = VOXB_F(v.w);
+	v = __ldg(src + 4); s.yz_a[2] = VOXB_F(v.x); s.yz_b[0] = VOXB_F(v.y); s.yz_b[1] = VOXB_F(v.z); s.yz_b[2] = VOXB_F(v.w);
+	v = __ldg(src + 5); s.yz_d[0] = VOXB_F(v.x); s.yz_d[1] = VOXB_F(v.y); s.yz_d[2] = VOXB_F(v.z); s.zx_a[0] = VOXB_F(v.w);
+	v = __ldg(src + 6); s.zx_a[1] = VOXB_F(v.x); s.zx_a[2] = VOXB_F(v.y); s.zx_b[0] = VOXB_F(v.z); s.zx_b[1] = VOXB_F(v.w);
+	v = __ldg(src + 7); s.zx_b[2] = VOXB_F(v.x); s.zx_d[0] = VOXB_F(v.y); s.zx_d[1] = VOXB_F(v.z); s.zx_d[2] = VOXB_F(v.w);
+	v = __ldg(src + 8);
+	s.x0 = (int)(v.x & 0xffffu); s.x1 = (int)(v.x >> 16); s.y0 = (int)(v.y & 0xffffu); s.y1 = (int)(v.y >> 16); s.z0 = (int)(v.z & 0xffffu); s.z1 = (int)(v.z >> 16);
+#undef VOXB_F
+}
+
 // Per-(y,z)-row values of the test (cpu_voxelizer.cpp:138-159 with the x-independent products
 // hoisted; each hoisted value is the same rounded product the reference recomputes per voxel).
 struct SurfRow {
@@ -348,10 +381,11 @@ __device__ __forceinline__ void load_tri_block_aos(const float* __restrict__ tri
 // Reserves, for every pushing lane of the warp, one queue slot and `items` consecutive work items with a
 // single packed atomicAdd ((slots << 32) | items).  Because both halves advance together, queue[] ends
 // up sorted by first-item, which is what lets the cooperative kernel binary-search item -> triangle.
-__device__ __forceinline__ void enqueue_warp(bool push, unsigned int items, unsigned int tri,
-                                             unsigned long long* counter, uint2* __restrict__ queue) {
+// Returns the caller's queue slot (0xffffffff when it did not push).
+__device__ __forceinline__ unsigned int enqueue_warp(bool push, unsigned int items, unsigned int tri,
+                                                     unsigned long long* counter, uint2* __restrict__ queue) {
 	const unsigned int pushers = __ballot_sync(0xffffffffu, push);
-	if (pushers == 0u) return;
+	if (pushers == 0u) return 0xffffffffu;
 	const int lane = threadIdx.x & 31;
 	const unsigned int mine = push ? items : 0u;
 	unsigned int incl = mine;
@@ -364,10 +398,10 @@ __device__ __forceinline__ void enqueue_warp(bool push, unsigned int items, unsi
 	unsigned long long base = 0ull;
 	if (lane == 0) base = atomicAdd(counter, ((unsigned long long)__popc(pushers) << 32) | (unsigned long long)total);
 	base = __shfl_sync(0xffffffffu, base, 0);
-	if (push) {
-		const unsigned int slot = (unsigned int)(base >> 32) + __popc(pushers & ((1u << lane) - 1u));
-		queue[slot] = make_uint2(tri, (unsigned int)base + (incl - mine));
-	}
+	if (!push) return 0xffffffffu;
+	const unsigned int slot = (unsigned int)(base >> 32) + __popc(pushers & ((1u << lane) - 1u));
+	queue[slot] = make_uint2(tri, (unsigned int)base + (incl - mine));
+	return slot;
 }
 
 }  // namespace voxb

@@ -16,6 +16,8 @@ struct Workspace {
 	unsigned long long* counters = nullptr;   // kNumCounters x u64, zeroed at the start of every call
 	uint2* queue = nullptr;                   // cooperative-path queue: {triangle, first work item}
 	size_t queue_cap = 0;                     // entries
+	uint4* setups = nullptr;                  // stored SurfSetup of the first setup_cap queued triangles (kSetupVec x 16 B each)
+	size_t setup_cap = 0;
 	unsigned int* scratch = nullptr;          // solid: mark table for ACCUMULATE / morton modes
 	size_t scratch_words = 0;
 	// optional per-phase timing (voxb200_set_profiling): a ring of event sets, one set per call
