@@ -184,3 +184,24 @@ def route_triangles(grid, tris, region, solid=False, morton=False, stream=0):
     flags = (MORTON if morton else 0) | (SOLID if solid else 0)
     check(_lib.lib().voxb200_route_triangles(C.byref(grid), C.c_void_p(tris.data_ptr()), flags, C.byref(region), C.byref(out), C.byref(n), C.c_void_p(stream)))
     return DeviceBuffer(out.value, n.value * 36), int(n.value)
+
+
+def voxelize_host_indexed(grid, host_verts, host_faces, host_table=None, solid=False, morton=False, region=None):
+    """End to end from the indexed mesh (numpy or pinned torch CPU tensors): H2D of vertices + faces, expansion on the
+    GPU, voxelization, D2H.  Returns (table, timing_ms[h2d+expand, voxelize, d2h, total])."""
+    def ptr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+    n_verts = (host_verts.numel() if hasattr(host_verts, "numel") else host_verts.size) // 3
+    if host_table is None:
+        if region is None:
+            nbytes = table_bytes(grid.gridsize[0])
+        else:
+            sx, sy, sz = (region.hi[k] - region.lo[k] for k in range(3))
+            nbytes = (sx * sy * sz + 31) // 32 * 4
+        host_table = np.empty(nbytes // 4, np.uint32)
+    timing = (C.c_float * 4)()
+    flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+    rp = C.byref(region) if region is not None else None
+    check(_lib.lib().voxb200_voxelize_host_indexed(C.byref(grid), C.c_void_p(ptr(host_verts)), n_verts, C.c_void_p(ptr(host_faces)),
+                                                   C.c_void_p(ptr(host_table)), flags, rp, timing))
+    return host_table, [float(t) for t in timing]

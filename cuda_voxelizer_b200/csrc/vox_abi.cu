@@ -22,6 +22,8 @@ thread_local char g_err[512] = "";
 struct HostPath {
 	float* d_tris = nullptr; size_t tris_bytes = 0;
 	unsigned int* d_table = nullptr; size_t table_bytes = 0;
+	float* d_verts = nullptr; size_t verts_bytes = 0;
+	int* d_faces = nullptr; size_t faces_bytes = 0;
 	void* pinned[2] = {nullptr, nullptr}; size_t pinned_bytes = 0;
 	cudaStream_t stream = nullptr, copy_stream = nullptr;
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -157,6 +159,17 @@ bool is_pinned_or_device(const void* p) {
 	cudaPointerAttributes attr;
 	if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return false; }
 	return attr.type == cudaMemoryTypeHost || attr.type == cudaMemoryTypeManaged || attr.type == cudaMemoryTypeDevice;
+}
+
+// Grows a persistent device buffer of the end-to-end path.
+template <typename T>
+int grow(T** p, size_t* have, size_t want) {
+	if (want <= *have) return VOXB200_OK;
+	if (*p) cudaFree(*p);
+	*p = nullptr; *have = 0;
+	CU(cudaMalloc(p, want));
+	*have = want;
+	return VOXB200_OK;
 }
 
 constexpr size_t kStageBytes = 32u << 20;   // pinned staging chunk for pageable host buffers
@@ -483,6 +496,48 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 	CU(cudaEventRecord(hp.ev[1], st));
 	const unsigned int path_flags = flags & (VOXB200_MORTON);
 	rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, path_flags, region, st);
+	if (rc) return rc;
+	CU(cudaEventRecord(hp.ev[2], st));
+	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));
+	CU(cudaEventRecord(hp.ev[3], st));
+	CU(cudaStreamSynchronize(st));
+	if (timing_ms) {
+		CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
+		CU(cudaEventElapsedTime(&timing_ms[1], hp.ev[1], hp.ev[2]));
+		CU(cudaEventElapsedTime(&timing_ms[2], hp.ev[2], hp.ev[3]));
+		CU(cudaEventElapsedTime(&timing_ms[3], hp.ev[0], hp.ev[3]));
+	}
+	return VOXB200_OK;
+}
+
+int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
+                                  unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]) {
+	if (!grid || !host_table || !host_verts || (!host_faces && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	HostPath& hp = g_hp[ws->device];
+	rc = ensure_host_path(hp);
+	if (rc) return rc;
+	GridParams g;
+	size_t region_words = 0;
+	rc = resolve_region(grid, region, (flags & VOXB200_MORTON) != 0, &g, &region_words);
+	if (rc) return rc;
+	const size_t n_faces = grid->n_triangles;
+	const size_t table_bytes = region_words * sizeof(unsigned int);
+	if ((rc = grow(&hp.d_verts, &hp.verts_bytes, n_verts * 3 * sizeof(float)))) return rc;
+	if ((rc = grow(&hp.d_faces, &hp.faces_bytes, n_faces * 3 * sizeof(int) + 16))) return rc;
+	if ((rc = grow(&hp.d_tris, &hp.tris_bytes, n_faces * 9 * sizeof(float) + 16))) return rc;
+	if ((rc = grow(&hp.d_table, &hp.table_bytes, table_bytes))) return rc;
+	cudaStream_t st = hp.stream;
+	CU(cudaEventRecord(hp.ev[0], st));
+	rc = h2d(hp, hp.d_verts, host_verts, n_verts * 3 * sizeof(float), st);
+	if (!rc) rc = h2d(hp, hp.d_faces, host_faces, n_faces * 3 * sizeof(int), st);
+	if (rc) return rc;
+	cudaError_t e = launch_expand_indexed(hp.d_verts, hp.d_faces, n_faces, n_verts, false, hp.d_tris, st);
+	if (e != cudaSuccess) return fail_cuda(e, "expand_indexed");
+	CU(cudaEventRecord(hp.ev[1], st));
+	rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, flags & VOXB200_MORTON, region, st);
 	if (rc) return rc;
 	CU(cudaEventRecord(hp.ev[2], st));
 	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));

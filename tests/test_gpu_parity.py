@@ -198,6 +198,8 @@ def test_voxelize_host_end_to_end(vb, golden, solid, morton):
     vb.voxelize_host(grid, pinned, out, solid=bool(solid), morton=bool(morton))
     assert np.array_equal(out.numpy().view(np.uint32), table)
     assert len(ms) == 4 and ms[3] > 0
+    table2, ms2 = vb.voxelize_host_indexed(grid, v, f, solid=bool(solid), morton=bool(morton))
+    assert np.array_equal(table2, table) and ms2[3] > 0
 
 
 def test_empty_and_degenerate_inputs(vb):
