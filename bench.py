@@ -250,22 +250,45 @@ def run_ours(args):
     pinned_faces = torch.from_numpy(np.ascontiguousarray(faces)).pin_memory()
     pinned_table = torch.empty(region_bytes // 4, dtype=torch.int32).pin_memory()
     e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(2):
-        vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)
-    barrier()
-    t0 = time.perf_counter()
-    e2e_dev_ms = 0.0
-    for _ in range(e2e_steps):
-        _, ms = vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)
-        e2e_dev_ms += ms[3]
-    torch.cuda.synchronize()
-    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
-    e2e_h2d_bytes = int(pinned_verts.numel() * 4 + pinned_faces.numel() * 4)
+    e2e_dev_ms, e2e_wall_ms, e2e_h2d_bytes = 0.0, 0.0, 0
+    if world == 1:
+        for _ in range(2):
+            vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            _, ms = vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)
+            e2e_dev_ms += ms[3]
+        torch.cuda.synchronize()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_h2d_bytes = int(pinned_verts.numel() * 4 + pinned_faces.numel() * 4)
+    e2e_api = "voxb200_voxelize_host_indexed (pinned host vertices+faces -> H2D -> expand -> voxelize -> D2H table slab)"
+    if world > 1:
+        # N > 1: the upload is sharded too.  Rank r holds 1/N of the soup in pinned memory, uploads only that, routes it
+        # on the GPU to the N slabs, swaps triangles in one all-to-all over NVLink, voxelizes its slab, reads it back.
+        from cuda_voxelizer_b200 import sharding
+        per = (n_tris + world - 1) // world
+        chunk = torch.from_numpy(np.ascontiguousarray(soup[rank * per: min(n_tris, (rank + 1) * per)]).reshape(-1)).pin_memory()
+        sv = sharding.ShardedHostVoxelizer(grid, solid=solid)
+        for _ in range(2):
+            sv(chunk, pinned_table)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_dev_ms = 0.0
+        for _ in range(e2e_steps):
+            e2e_dev_ms += sv(chunk, pinned_table)
+        torch.cuda.synchronize()
+        e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+        e2e_h2d_bytes = int(chunk.numel() * 4)
+        e2e_api = "sharding.ShardedHostVoxelizer (pinned 1/N soup -> H2D -> route x N -> NCCL all-to-all -> voxelize -> D2H table slab)"
     # device-event total per step (H2D start -> D2H end), max over ranks; wall kept alongside
     te = torch.tensor([e2e_dev_ms / e2e_steps, e2e_wall_ms / e2e_steps], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_ms, e2e_wall = float(te[0].item()), float(te[1].item())
+    e2e_table_check = None
+    if world > 1:
+        e2e_table_check = bool(torch.equal(pinned_table, table.cpu()))
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- N > 1: slab gather over NVLink (NCCL all-gather), timed apart; the gathered table is parity-checked ----
@@ -354,7 +377,7 @@ def run_ours(args):
                    "l2": "inputs larger than L2 (%.0f MB soup + %.0f MB table slab per GPU vs 126 MB L2)" % (tri_bytes / 1e6, slab_bytes / 1e6)},
         "e2e": {"value": round(n_tris / e2e_ms / 1e3, 2), "unit": "Mtri/s", "h2d_bytes_per_step": e2e_h2d_bytes, "d2h_bytes_per_step": int(slab_bytes),
                 "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall, 3), "steps": e2e_steps,
-                "api": "voxb200_voxelize_host_indexed (pinned host vertices+faces -> H2D -> expand -> voxelize -> D2H table slab), per rank"},
+                "api": e2e_api + ", per rank", "slab_matches_device_path": e2e_table_check},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "counters": counters, "parity": check,
     }

@@ -205,3 +205,14 @@ def voxelize_host_indexed(grid, host_verts, host_faces, host_table=None, solid=F
     check(_lib.lib().voxb200_voxelize_host_indexed(C.byref(grid), C.c_void_p(ptr(host_verts)), n_verts, C.c_void_p(ptr(host_faces)),
                                                    C.c_void_p(ptr(host_table)), flags, rp, timing))
     return host_table, [float(t) for t in timing]
+
+
+def route_triangles_multi(grid, tris, regions, out, solid=False, morton=False, stream=None):
+    """Route a device soup to several regions at once into the preallocated CUDA tensor ``out`` (float32, capacity
+    out.numel() // 9 triangles), segments back to back in region order.  Returns the per-region triangle counts."""
+    arr = (Region * len(regions))(*regions)
+    counts = (C.c_size_t * len(regions))()
+    flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+    check(_lib.lib().voxb200_route_triangles_multi(C.byref(grid), C.c_void_p(tris.data_ptr()), flags, arr, len(regions),
+                                                   C.c_void_p(out.data_ptr()), out.numel() // 9, counts, _stream_ptr(stream)))
+    return [int(c) for c in counts]

@@ -116,6 +116,104 @@ __global__ void __launch_bounds__(kUpBlock) route_kernel(const GridParams g, con
 	}
 }
 
+// Multi-region routing (N ranks): pass 1 computes, per triangle, the bit mask of the regions it can touch and counts
+// per region; pass 2 appends each triangle to the segment of every region in its mask.  Regions are boxes.
+struct RouteBoxes {
+	int lo[32][3];
+	int hi[32][3];
+	int n;
+};
+
+template <bool SOLID>
+__device__ __forceinline__ unsigned int route_mask(const GridParams& g, const RouteBoxes& rb, const Tri& t_model) {
+	Tri ts = t_model;
+	shift_tri(ts, g);
+	int x0, x1, y0, y1, z0, z1;
+	if (SOLID) {
+		SolidSetup s;
+		solid_setup(ts, g, s);
+		if (s.skip) return 0u;
+		x0 = 0; x1 = g.G - 1; y0 = s.y0; y1 = s.y1; z0 = s.z0; z1 = s.z1;
+	} else {
+		SurfSetup s;
+		surf_bbox(ts, g, s);
+		x0 = s.x0; x1 = s.x1; y0 = s.y0; y1 = s.y1; z0 = s.z0; z1 = s.z1;
+	}
+	unsigned int m = 0u;
+	for (int r = 0; r < rb.n; r++) {
+		const bool hit = max(x0, rb.lo[r][0]) <= min(x1, rb.hi[r][0] - 1) && max(y0, rb.lo[r][1]) <= min(y1, rb.hi[r][1] - 1) &&
+		                 max(z0, rb.lo[r][2]) <= min(z1, rb.hi[r][2] - 1);
+		m |= hit ? (1u << r) : 0u;
+	}
+	return m;
+}
+
+template <bool SOLID>
+__global__ void __launch_bounds__(kUpBlock) route_count_kernel(const GridParams g, const RouteBoxes rb, const float* __restrict__ soup,
+                                                               unsigned int* __restrict__ masks, unsigned long long* __restrict__ counts) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * kUpBlock + threadIdx.x;
+	unsigned int m = 0u;
+	if (i < g.n_tris) {
+		Tri t;
+		load_tri_aos(soup, i, t);
+		m = route_mask<SOLID>(g, rb, t);
+		masks[i] = m;
+	}
+	for (int r = 0; r < rb.n; r++) {
+		const unsigned int b = __ballot_sync(0xffffffffu, (m >> r) & 1u);
+		if (b && (threadIdx.x & 31) == 0) atomicAdd(counts + r, (unsigned long long)__popc(b));
+	}
+}
+
+__global__ void __launch_bounds__(kUpBlock) route_scatter_kernel(unsigned long long n_tris, int n_regions, const float* __restrict__ soup,
+                                                                 const unsigned int* __restrict__ masks, float* __restrict__ out,
+                                                                 unsigned long long* __restrict__ cursors /* pre-set to segment starts */) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * kUpBlock + threadIdx.x;
+	const unsigned int m = i < n_tris ? masks[i] : 0u;
+	const int lane = threadIdx.x & 31;
+	float v[9];
+	if (m) {
+#pragma unroll
+		for (int k = 0; k < 9; k++) v[k] = __ldg(soup + 9ull * i + k);
+	}
+	for (int r = 0; r < n_regions; r++) {
+		const bool mine = (m >> r) & 1u;
+		const unsigned int b = __ballot_sync(0xffffffffu, mine);
+		if (!b) continue;
+		unsigned long long base = 0ull;
+		if (lane == 0) base = atomicAdd(cursors + r, (unsigned long long)__popc(b));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (mine) {
+			float* o = out + 9ull * (base + __popc(b & ((1u << lane) - 1u)));
+#pragma unroll
+			for (int k = 0; k < 9; k++) o[k] = v[k];
+		}
+	}
+}
+
+cudaError_t launch_route_count(const GridParams& g, bool solid, const int (*lo)[3], const int (*hi)[3], int n_regions, const float* d_soup,
+                               unsigned int* d_masks, unsigned long long* d_counts, cudaStream_t st) {
+	RouteBoxes rb;
+	rb.n = n_regions;
+	for (int r = 0; r < n_regions; r++) for (int k = 0; k < 3; k++) { rb.lo[r][k] = lo[r][k]; rb.hi[r][k] = hi[r][k]; }
+	cudaError_t err = cudaMemsetAsync(d_counts, 0, 32 * sizeof(unsigned long long), st);
+	if (err != cudaSuccess || g.n_tris == 0) return err;
+	const unsigned blocks = (unsigned)((g.n_tris + kUpBlock - 1) / kUpBlock);
+	if (solid) route_count_kernel<true><<<blocks, kUpBlock, 0, st>>>(g, rb, d_soup, d_masks, d_counts);
+	else route_count_kernel<false><<<blocks, kUpBlock, 0, st>>>(g, rb, d_soup, d_masks, d_counts);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
+cudaError_t launch_route_scatter(unsigned long long n_tris, int n_regions, const float* d_soup, const unsigned int* d_masks, float* d_out,
+                                 unsigned long long* d_cursors, cudaStream_t st) {
+	if (n_tris == 0) return cudaSuccess;
+	const unsigned blocks = (unsigned)((n_tris + kUpBlock - 1) / kUpBlock);
+	route_scatter_kernel<<<blocks, kUpBlock, 0, st>>>(n_tris, n_regions, d_soup, d_masks, d_out, d_cursors);
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st) {
 	cudaError_t err = cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), st);
 	if (err != cudaSuccess || g.n_tris == 0) return err;

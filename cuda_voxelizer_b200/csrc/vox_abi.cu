@@ -452,6 +452,45 @@ int voxb200_route_triangles(const voxb200_grid* grid, const float* d_tris9, unsi
 	return VOXB200_OK;
 }
 
+int voxb200_route_triangles_multi(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* regions,
+                                  int n_regions, float* d_out, size_t out_capacity, size_t* counts, void* stream) {
+	if (!grid || !regions || !counts || (!d_tris9 && grid->n_triangles) || (!d_out && out_capacity)) return fail(VOXB200_EINVAL, "NULL pointer");
+	if (n_regions < 1 || n_regions > 32) return fail(VOXB200_EINVAL, "1..32 regions per call (got %d)", n_regions);
+	if (flags & VOXB200_TRIS_SOA4) return fail(VOXB200_EINVAL, "routing takes the 9-float soup");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	GridParams g;
+	size_t words = 0;
+	int lo[32][3], hi[32][3];
+	for (int r = 0; r < n_regions; r++) {
+		rc = resolve_region(grid, &regions[r], (flags & VOXB200_MORTON) != 0, &g, &words);      // validates each region
+		if (rc) return rc;
+		for (int k = 0; k < 3; k++) { lo[r][k] = regions[r].lo[k]; hi[r][k] = regions[r].hi[k]; }
+	}
+	if (grid->n_triangles > ws->route_cap) {
+		if (ws->route_masks) cudaFree(ws->route_masks);
+		ws->route_masks = nullptr; ws->route_cap = 0;
+		CU(cudaMalloc(&ws->route_masks, grid->n_triangles * sizeof(unsigned int)));
+		ws->route_cap = grid->n_triangles;
+	}
+	if (!ws->route_counts) CU(cudaMalloc(&ws->route_counts, 64 * sizeof(unsigned long long)));
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaError_t e = launch_route_count(g, (flags & VOXB200_SOLID) != 0, lo, hi, n_regions, d_tris9, ws->route_masks, ws->route_counts, st);
+	unsigned long long c[32];
+	if (e == cudaSuccess) e = cudaMemcpyAsync(c, ws->route_counts, sizeof(c), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e != cudaSuccess) return fail_cuda(e, "voxb200_route_triangles_multi (count)");
+	unsigned long long cursors[32], total = 0;
+	for (int r = 0; r < 32; r++) { cursors[r] = total; if (r < n_regions) { counts[r] = (size_t)c[r]; total += c[r]; } }
+	if (total > out_capacity) return fail(VOXB200_EINVAL, "routed triangles (%llu) exceed the output capacity (%zu)", total, out_capacity);
+	e = cudaMemcpyAsync(ws->route_counts + 32, cursors, sizeof(cursors), cudaMemcpyHostToDevice, st);
+	if (e == cudaSuccess) e = launch_route_scatter(grid->n_triangles, n_regions, d_tris9, ws->route_masks, d_out, ws->route_counts + 32, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);      // `cursors` lives on this stack frame
+	if (e != cudaSuccess) return fail_cuda(e, "voxb200_route_triangles_multi (scatter)");
+	return VOXB200_OK;
+}
+
 int voxb200_surface(const voxb200_grid* grid, const float* d_tris, unsigned int* d_table, unsigned int flags,
                     const voxb200_region* region, void* stream) {
 	return run_path(false, grid, d_tris, d_table, flags, region, (cudaStream_t)stream);

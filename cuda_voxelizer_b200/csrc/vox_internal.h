@@ -18,6 +18,9 @@ struct Workspace {
 	size_t queue_cap = 0;                     // entries
 	uint4* setups = nullptr;                  // stored SurfSetup of the first setup_cap queued triangles (kSetupVec x 16 B each)
 	size_t setup_cap = 0;
+	unsigned int* route_masks = nullptr;      // multi-region routing: per-triangle region mask
+	size_t route_cap = 0;
+	unsigned long long* route_counts = nullptr;   // 32 counters + 32 cursors
 	unsigned int* scratch = nullptr;          // solid: mark table for ACCUMULATE / morton modes
 	size_t scratch_words = 0;
 	// optional per-phase timing (voxb200_set_profiling): a ring of event sets, one set per call
@@ -64,6 +67,10 @@ cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tri
 cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t n_verts,
                                   bool soa4, float* d_out, cudaStream_t st);
 cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st);
+cudaError_t launch_route_count(const GridParams& g, bool solid, const int (*lo)[3], const int (*hi)[3], int n_regions, const float* d_soup,
+                               unsigned int* d_masks, unsigned long long* d_counts, cudaStream_t st);
+cudaError_t launch_route_scatter(unsigned long long n_tris, int n_regions, const float* d_soup, const unsigned int* d_masks, float* d_out,
+                                 unsigned long long* d_cursors, cudaStream_t st);
 cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);
 
 }  // namespace voxb

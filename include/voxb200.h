@@ -123,6 +123,15 @@ int voxb200_upload_indexed(const float* host_verts, size_t n_verts, const int32_
 int voxb200_route_triangles(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* region,
                             float** d_routed, size_t* n_routed, void* stream);
 
+/*
+ * Routing to several regions at once (every rank routes ITS share of the mesh to all N ranks before an all-to-all):
+ * d_out receives, back to back in region order, the triangles that can touch regions[0], regions[1], …;
+ * counts[r] (host) = triangles in segment r; a triangle overlapping two regions appears in both segments.
+ * out_capacity is in triangles.  n_regions <= 32.  Synchronises `stream`.
+ */
+int voxb200_route_triangles_multi(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* regions,
+                                  int n_regions, float* d_out, size_t out_capacity, size_t* counts, void* stream);
+
 /* ---- the hot path --------------------------------------------------------------------------- */
 /*
  * d_tris and d_table are device-accessible pointers (cudaMalloc or cudaMallocManaged).  `stream`

@@ -164,6 +164,32 @@ def test_routed_triangles_give_same_region(vb, name, g, solid):
     assert total >= (len(f) if not solid else 1) and total <= 2 * len(f)
 
 
+@pytest.mark.parametrize("solid,morton", [(0, 0), (1, 0), (0, 1)])
+def test_multi_region_routing(vb, solid, morton):
+    """voxb200_route_triangles_multi: one pass routes a soup to all N regions; voxelizing segment r over region r
+    reproduces region r of the full table (what every rank does after the all-to-all)."""
+    import copy
+    name, g, n = "icosphere:64:128", 256, 8
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    full = fn(grid, d_tris, morton=bool(morton)).clone()
+    regions = [vb.partition(g, morton, p, n)[0] for p in range(n)]
+    out = torch.empty(2 * d_tris.numel(), device="cuda")
+    counts = vb.route_triangles_multi(grid, d_tris, regions, out, solid=bool(solid), morton=bool(morton))
+    assert len(counts) == n and sum(counts) <= 2 * len(f) and (solid or sum(counts) >= len(f))
+    parts, off = [], 0
+    for p in range(n):
+        g2 = copy.copy(grid)
+        g2.n_triangles = counts[p]
+        seg = out[9 * off: 9 * (off + counts[p])] if counts[p] else torch.zeros(9, device="cuda")
+        parts.append(fn(g2, seg.contiguous(), morton=bool(morton), region=regions[p]).clone())
+        off += counts[p]
+    assert torch.equal(torch.cat(parts), full)
+    with pytest.raises(vb.VoxError):
+        vb.route_triangles_multi(grid, d_tris, regions, out[:9], solid=bool(solid), morton=bool(morton))   # capacity too small
+
+
 def test_upload_paths(vb):
     """Triangle upload (main.cpp:61-80 replaced): soup and indexed uploads, AoS and SoA4, plus the
     device bbox reduction, all lead to the same table as torch-owned memory."""

@@ -50,6 +50,13 @@ def _worker(rank, world, port, solid, result_path):
         gathered = sharding.gather_table(mine).numpy().view(np.uint32)
         want = fn(soup, bb_min, unit, g)
         ok = bool(np.array_equal(gathered, want))
+        # all-to-all of routed triangles: rank r sends r+1 triangles tagged (r, dst) to every dst
+        send_counts = [rank + 1] * world
+        send = torch.cat([torch.full((9 * (rank + 1),), float(100 * rank + dst)) for dst in range(world)])
+        recv, recv_counts = sharding.exchange_routed(send, send_counts)
+        ok = ok and recv_counts == [src + 1 for src in range(world)]
+        want_recv = torch.cat([torch.full((9 * (src + 1),), float(100 * src + rank)) for src in range(world)])
+        ok = ok and bool(torch.equal(recv, want_recv))
         on0 = sharding.gather_table_to(mine, dst=0)
         if rank == 0:
             ok = ok and bool(np.array_equal(on0.numpy().view(np.uint32), want))
