@@ -1,5 +1,5 @@
 #!/bin/bash
-# usage: gpurun_bench.sh <tag> [extra bench args]  — short bench of the headline config + parity check
+# usage: scripts/gpurun_bench.sh <tag> [extra bench args]  — short bench of the headline config + parity check
 tag=$1; shift
 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline "$@" > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
 python - <<PY
