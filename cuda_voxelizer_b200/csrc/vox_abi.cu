@@ -5,7 +5,6 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
-#include <mutex>
 
 #include "../../include/voxb200.h"
 #include "vox_internal.h"
@@ -25,12 +24,11 @@ struct HostPath {
 	float* d_verts = nullptr; size_t verts_bytes = 0;
 	int* d_faces = nullptr; size_t faces_bytes = 0;
 	void* pinned[2] = {nullptr, nullptr}; size_t pinned_bytes = 0;
-	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t buf_free[2] = {nullptr, nullptr};
 	bool buf_busy[2] = {false, false};     // a copy out of pinned[b] may still be in flight
 	int next_buf = 0;
-	cudaEvent_t chunk_ready = nullptr;
 };
 HostPath g_hp[kMaxDevices];
 
@@ -177,10 +175,8 @@ constexpr size_t kStageBytes = 32u << 20;   // pinned staging chunk for pageable
 int ensure_host_path(HostPath& hp) {
 	if (!hp.stream) {
 		CU(cudaStreamCreateWithFlags(&hp.stream, cudaStreamNonBlocking));
-		CU(cudaStreamCreateWithFlags(&hp.copy_stream, cudaStreamNonBlocking));
 		for (auto& e : hp.ev) CU(cudaEventCreate(&e));
 		for (auto& e : hp.buf_free) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-		CU(cudaEventCreateWithFlags(&hp.chunk_ready, cudaEventDisableTiming));
 	}
 	return VOXB200_OK;
 }

@@ -10,6 +10,11 @@
  * There is NO CPU fallback behind this ABI: without a CUDA device every compute entry point fails
  * with VOXB200_ENODEVICE.
  *
+ * Threading: like the reference (which writes __constant__ LUTs and uses the legacy default stream), the library
+ * keeps per-device scratch (work queue, counters, staging buffers) and is NOT re-entrant: use one host thread per
+ * device, or serialise calls that target the same device.  Calls on different streams of one device must not
+ * overlap for the same reason.
+ *
  * Reference interfaces replaced (file:line into the reference tree):
  *   voxb200_init / voxb200_device_count ... initCuda()                    src/util_cuda.cpp:4-42
  *   voxb200_make_grid .................... createMeshBBCube + voxinfo     src/util.h:56-61, 80-110 (main.cpp:184-186)
