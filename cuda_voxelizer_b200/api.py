@@ -216,3 +216,17 @@ def route_triangles_multi(grid, tris, regions, out, solid=False, morton=False, s
     check(_lib.lib().voxb200_route_triangles_multi(C.byref(grid), C.c_void_p(tris.data_ptr()), flags, arr, len(regions),
                                                    C.c_void_p(out.data_ptr()), out.numel() // 9, counts, _stream_ptr(stream)))
     return [int(c) for c in counts]
+
+
+def extract_voxels(table, first_voxel=0, stream=None):
+    """Device-side compaction of a table (CUDA int32 tensor) into the ascending indices of its set voxels.
+    Returns a numpy uint64 array (copied to the host)."""
+    out = C.c_void_p(0)
+    n = C.c_size_t(0)
+    check(_lib.lib().voxb200_extract_voxels(C.c_void_p(table.data_ptr()), table.numel(), int(first_voxel), C.byref(out), C.byref(n), _stream_ptr(stream)))
+    buf = DeviceBuffer(out.value, n.value * 8)
+    host = np.empty(n.value, np.uint64)
+    if n.value:
+        check(_lib.lib().voxb200_memcpy_d2h(C.c_void_p(host.ctypes.data), C.c_void_p(buf.ptr), n.value * 8, _stream_ptr(stream)))
+    buf.close()
+    return host

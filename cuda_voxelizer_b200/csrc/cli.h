@@ -28,11 +28,18 @@ inline bool check_voxel(size_t x, size_t y, size_t z, const uint3 gridsize, cons
 	return (vtable[location / 32] >> (31 - (location % 32))) & 1u;
 }
 
-// Output formats of util_io.cpp, same file names (note they append to the FULL input file name, main.cpp:246-257).
+// The set voxels of a (linear-order) table as ascending voxel indices x + G*y + G*G*z — what voxb200_extract_voxels returns.
+struct VoxelList {
+	std::vector<uint64_t> indices;
+	unsigned int gridsize;
+};
+
+// Output formats of util_io.cpp, same file names (note they append to the FULL input file name, main.cpp:246-257) and
+// the same bytes, produced from the voxel list instead of G^3 checkVoxel() calls.
 void write_binary(const void* data, size_t bytes, const std::string& base_filename);                       // -o morton
-void write_binvox(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename);       // -o binvox
-void write_obj_pointcloud(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename);  // -o obj_points
-void write_obj_cubes(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename);    // -o obj
-void write_vox(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename);          // -o vox
+void write_binvox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);             // -o binvox
+void write_obj_pointcloud(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);     // -o obj_points
+void write_obj_cubes(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);          // -o obj
+void write_vox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);                // -o vox
 
 }  // namespace voxcli

@@ -154,20 +154,43 @@ int main(int argc, char* argv[]) {
 	cudaEventElapsedTime(&ms, e0, e1);
 	printf("[Perf] Voxelization GPU time: %.1f ms\n", ms);
 
-	std::vector<unsigned int> vtable(vtable_size / 4);
-	rc = voxb200_memcpy_d2h(vtable.data(), d_table, vtable_size, nullptr);
-	if (rc) die_abi("voxb200_memcpy_d2h", rc);
+	// -o morton dumps the raw table (util_io.cpp:192-200).  Every other writer only needs the SET voxels: they are
+	// compacted on the GPU and only that list crosses PCIe.
+	std::vector<unsigned int> vtable;
+	VoxelList voxels;
+	voxels.gridsize = opt.gridsize;
+	const double t_rb = now_ms();
+	if (morton) {
+		vtable.resize(vtable_size / 4);
+		rc = voxb200_memcpy_d2h(vtable.data(), d_table, vtable_size, nullptr);
+		if (rc) die_abi("voxb200_memcpy_d2h", rc);
+	} else {
+		uint64_t* d_idx = nullptr;
+		size_t n_set = 0;
+		rc = voxb200_extract_voxels(d_table, vtable_size / 4, 0, &d_idx, &n_set, nullptr);
+		if (rc) die_abi("voxb200_extract_voxels", rc);
+		voxels.indices.resize(n_set);
+		if (n_set) {
+			rc = voxb200_memcpy_d2h(voxels.indices.data(), d_idx, n_set * sizeof(uint64_t), nullptr);
+			if (rc) die_abi("voxb200_memcpy_d2h", rc);
+		}
+		voxb200_free(d_idx);
+		printf("[Voxel Grid] %zu voxels set \n", n_set);
+	}
+	printf("[Perf] Table read-back: %.1f ms \n", now_ms() - t_rb);
 	voxb200_free(d_tris);
 	voxb200_free(d_table);
 
 	printf("\n## FILE OUTPUT \n");
+	const double t_out = now_ms();
 	switch (opt.format) {
 		case Format::morton: write_binary(vtable.data(), vtable_size, opt.filename); break;
-		case Format::binvox: write_binvox(vtable.data(), info, opt.filename); break;
-		case Format::obj_points: write_obj_pointcloud(vtable.data(), info, opt.filename); break;
-		case Format::obj_cubes: write_obj_cubes(vtable.data(), info, opt.filename); break;
-		case Format::vox: write_vox(vtable.data(), info, opt.filename); break;
+		case Format::binvox: write_binvox(voxels, info, opt.filename); break;
+		case Format::obj_points: write_obj_pointcloud(voxels, info, opt.filename); break;
+		case Format::obj_cubes: write_obj_cubes(voxels, info, opt.filename); break;
+		case Format::vox: write_vox(voxels, info, opt.filename); break;
 	}
+	printf("[Perf] File output: %.1f ms \n", now_ms() - t_out);
 	printf("\n## STATS \n");
 	printf("[Perf] Total runtime: %.1f ms \n", now_ms() - t_start);
 	return 0;

@@ -587,6 +587,33 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 	return VOXB200_OK;
 }
 
+int voxb200_extract_voxels(const unsigned int* d_table, size_t table_words, uint64_t first_voxel, uint64_t** d_indices, size_t* count, void* stream) {
+	if (!d_table || !d_indices || !count) return fail(VOXB200_EINVAL, "NULL pointer");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t blocks = extract_blocks(table_words);
+	unsigned int* d_counts = nullptr;
+	unsigned long long* d_offsets = nullptr;
+	unsigned long long* d_out = nullptr;
+	cudaError_t e = cudaMalloc(&d_counts, (blocks + 1) * sizeof(unsigned int));
+	if (e == cudaSuccess) e = cudaMalloc(&d_offsets, (blocks + 1) * sizeof(unsigned long long));
+	unsigned long long total = 0;
+	if (e == cudaSuccess) e = launch_extract_count(d_table, table_words, d_counts, d_offsets, st);
+	if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_offsets + blocks, sizeof(total), cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	if (e == cudaSuccess) e = cudaMalloc(&d_out, (total ? total : 1) * sizeof(unsigned long long));
+	if (e == cudaSuccess) e = launch_extract_write(d_table, table_words, d_offsets, first_voxel, d_out, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	cudaFree(d_counts);
+	cudaFree(d_offsets);
+	if (e != cudaSuccess) { cudaFree(d_out); return fail_cuda(e, "voxb200_extract_voxels"); }
+	*d_indices = reinterpret_cast<uint64_t*>(d_out);
+	*count = (size_t)total;
+	return VOXB200_OK;
+}
+
 uint64_t voxb200_launch_count(int reset) {
 	const uint64_t v = g_launch_count;
 	if (reset) g_launch_count = 0;

@@ -71,6 +71,11 @@ cudaError_t launch_route_count(const GridParams& g, bool solid, const int (*lo)[
                                unsigned int* d_masks, unsigned long long* d_counts, cudaStream_t st);
 cudaError_t launch_route_scatter(unsigned long long n_tris, int n_regions, const float* d_soup, const unsigned int* d_masks, float* d_out,
                                  unsigned long long* d_cursors, cudaStream_t st);
+// Table consumer: set voxels -> ascending voxel indices
+size_t extract_blocks(size_t n_words);
+cudaError_t launch_extract_count(const unsigned int* d_table, size_t n_words, unsigned int* d_counts, unsigned long long* d_offsets, cudaStream_t st);
+cudaError_t launch_extract_write(const unsigned int* d_table, size_t n_words, const unsigned long long* d_offsets, unsigned long long first_voxel,
+                                 unsigned long long* d_out, cudaStream_t st);
 cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);
 
 }  // namespace voxb

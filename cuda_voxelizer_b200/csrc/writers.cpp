@@ -1,5 +1,7 @@
 // writers.cpp — the five output formats of the reference CLI (src/util_io.cpp), restated for the drop-in tool.
-// They consume the bit table on the host through check_voxel(), i.e. they depend only on the layout contract.
+// The reference walks all G^3 voxels through checkVoxel() in every writer (util_io.cpp:116-128, 167-181, 219-240,
+// 267-281).  Here the GPU compacts the set voxels first (voxb200_extract_voxels) and the writers walk that list,
+// re-sorted on the host into each format's own traversal order — same bytes out, O(set voxels) instead of O(G^3).
 // File names follow the reference exactly (they are appended to the full input file name, main.cpp:246-257).
 //   morton ...... <file>.bin                 raw table dump                       (util_io.cpp:192-200)
 //   binvox ...... <file>_<G>.binvox          header + RLE, x -> z -> y order      (util_io.cpp:202-246)
@@ -13,6 +15,7 @@
 #include <cstring>
 #include <fstream>
 #include <map>
+#include <cstdint>
 #include <string>
 #include <vector>
 
@@ -27,7 +30,34 @@ void write_binary(const void* data, size_t bytes, const std::string& base_filena
 	out.write(static_cast<const char*>(data), (std::streamsize)bytes);
 }
 
-void write_binvox(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename) {
+// Ascending sort of 64-bit keys below 2^bits, LSD radix with 11-bit digits.
+static void radix_sort(std::vector<uint64_t>& keys, int bits) {
+	std::vector<uint64_t> tmp(keys.size());
+	for (int shift = 0; shift < bits; shift += 11) {
+		size_t hist[2049] = {0};
+		for (uint64_t k : keys) hist[((k >> shift) & 2047u) + 1]++;
+		for (int i = 0; i < 2048; i++) hist[i + 1] += hist[i];
+		for (uint64_t k : keys) tmp[hist[(k >> shift) & 2047u]++] = k;
+		keys.swap(tmp);
+	}
+}
+static int bits_for(uint64_t n) { int b = 1; while ((1ull << b) < n) b++; return b; }
+
+// Re-keys the voxel list (linear idx = x + G*y + G*G*z) as (a*G + b)*G + c for a traversal order a -> b -> c and sorts it.
+enum class Axis { x, y, z };
+static std::vector<uint64_t> traversal_keys(const VoxelList& vox, Axis a, Axis b, Axis c) {
+	const uint64_t G = vox.gridsize;
+	std::vector<uint64_t> keys(vox.indices.size());
+	for (size_t i = 0; i < keys.size(); i++) {
+		const uint64_t idx = vox.indices[i];
+		const uint64_t p[3] = {idx % G, (idx / G) % G, idx / (G * G)};
+		keys[i] = (p[(int)a] * G + p[(int)b]) * G + p[(int)c];
+	}
+	radix_sort(keys, bits_for(G * G * G));
+	return keys;
+}
+
+void write_binvox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
 	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + ".binvox";
 	fprintf(stdout, "[I/O] Writing data in binvox format to %s \n", name.c_str());
 	std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
@@ -37,56 +67,57 @@ void write_binvox(const unsigned int* vtable, const voxinfo& info, const std::st
 	out << "translate " << info.bbox.min.x << " " << info.bbox.min.y << " " << info.bbox.min.z << std::endl;
 	out << "scale " << std::max(std::max(sx, sy), sz) << std::endl;
 	out << "data" << std::endl;
-	// run-length pairs (value, count<=255), voxels visited x-major, then z, then y
+	// (value, count <= 255) pairs over the voxels visited x-major, then z, then y (util_io.cpp:219-240): a run of L equal
+	// voxels comes out as (v,255) pairs and a remainder, exactly what the reference's counter produces
+	const uint64_t G = vox.gridsize, total = G * G * G;
+	const std::vector<uint64_t> keys = traversal_keys(vox, Axis::x, Axis::z, Axis::y);
 	std::vector<char> buf;
 	buf.reserve(1 << 20);
-	char value = 0;
-	unsigned char run = 0;
-	bool first = true;
-	for (size_t x = 0; x < info.gridsize.x; x++)
-		for (size_t z = 0; z < info.gridsize.z; z++)
-			for (size_t y = 0; y < info.gridsize.y; y++) {
-				const char v = check_voxel(x, y, z, info.gridsize, vtable) ? 1 : 0;
-				if (first) { value = v; buf.push_back(value); run = 1; first = false; continue; }
-				if (v != value || run == 255) {
-					buf.push_back((char)run);
-					run = 1;
-					value = v;
-					buf.push_back(value);
-				} else {
-					run++;
-				}
-				if (buf.size() >= (1u << 20) - 4) { out.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
-			}
-	buf.push_back((char)run);
+	auto emit = [&](char value, uint64_t len) {
+		while (len > 255) { buf.push_back(value); buf.push_back((char)255); len -= 255; }
+		buf.push_back(value); buf.push_back((char)len);
+		if (buf.size() >= (1u << 20) - 600) { out.write(buf.data(), (std::streamsize)buf.size()); buf.clear(); }
+	};
+	uint64_t pos = 0;
+	for (size_t i = 0; i < keys.size();) {
+		size_t j = i;
+		while (j + 1 < keys.size() && keys[j + 1] == keys[j] + 1) j++;
+		if (keys[i] > pos) emit(0, keys[i] - pos);
+		emit(1, keys[j] - keys[i] + 1);
+		pos = keys[j] + 1;
+		i = j + 1;
+	}
+	if (pos < total) emit(0, total - pos);
 	out.write(buf.data(), (std::streamsize)buf.size());
 }
 
-void write_obj_pointcloud(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename) {
+void write_obj_pointcloud(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
 	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + "_pointcloud.obj";
 	fprintf(stdout, "[I/O] Writing data in obj point cloud format to %s \n", name.c_str());
-	std::ofstream out(name.c_str(), std::ios::out);
-	for (size_t x = 0; x < info.gridsize.x; x++)
-		for (size_t y = 0; y < info.gridsize.y; y++)
-			for (size_t z = 0; z < info.gridsize.z; z++)
-				if (check_voxel(x, y, z, info.gridsize, vtable)) out << "v " << (x + 0.5) << " " << (y + 0.5) << " " << (z + 0.5) << "\n";
+	FILE* out = fopen(name.c_str(), "w");
+	if (!out) return;
+	const uint64_t G = vox.gridsize;
+	for (uint64_t k : traversal_keys(vox, Axis::x, Axis::y, Axis::z))      // x -> y -> z like util_io.cpp:167-181
+		fprintf(out, "v %g %g %g\n", (double)(k / (G * G)) + 0.5, (double)((k / G) % G) + 0.5, (double)(k % G) + 0.5);   // %g == ostream default
+	fclose(out);
 }
 
-void write_obj_cubes(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename) {
+void write_obj_cubes(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
 	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + "_voxels.obj";
 	fprintf(stdout, "[I/O] Writing data in obj voxels format to file %s \n", name.c_str());
-	std::ofstream out(name.c_str(), std::ios::out);
+	FILE* out = fopen(name.c_str(), "w");
+	if (!out) return;
 	// corner order and relative (negative) face indices as in util_io.cpp:45-89: v8 is written first, so corner i is -i
 	static const int corner[8][3] = {{1, 1, 0}, {0, 1, 0}, {1, 0, 0}, {0, 0, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};   // v8..v1
 	static const int face[12][3] = {{-1, -3, -4}, {-1, -4, -2}, {-4, -3, -6}, {-4, -6, -5}, {-3, -1, -8}, {-3, -8, -6},
 	                                {-1, -2, -7}, {-1, -7, -8}, {-2, -4, -5}, {-2, -5, -7}, {-5, -6, -8}, {-5, -8, -7}};
-	for (size_t x = 0; x < info.gridsize.x; x++)
-		for (size_t y = 0; y < info.gridsize.y; y++)
-			for (size_t z = 0; z < info.gridsize.z; z++) {
-				if (!check_voxel(x, y, z, info.gridsize, vtable)) continue;
-				for (const auto& c : corner) out << "v " << (long)x + c[0] << " " << (long)y + c[1] << " " << (long)z + c[2] << "\n";
-				for (const auto& f : face) out << "f " << f[0] << " " << f[1] << " " << f[2] << "\n";
-			}
+	const uint64_t G = vox.gridsize;
+	for (uint64_t k : traversal_keys(vox, Axis::x, Axis::y, Axis::z)) {
+		const long x = (long)(k / (G * G)), y = (long)((k / G) % G), z = (long)(k % G);
+		for (const auto& c : corner) fprintf(out, "v %ld %ld %ld\n", x + c[0], y + c[1], z + c[2]);
+		for (const auto& f : face) fprintf(out, "f %d %d %d\n", f[0], f[1], f[2]);
+	}
+	fclose(out);
 }
 
 // ---- MagicaVoxel .vox (format 150): models of at most 256^3 placed by a transform/group/shape scene graph
@@ -102,21 +133,19 @@ void put_chunk(std::vector<char>& out, const char id[4], const std::vector<char>
 }
 }  // namespace
 
-void write_vox(const unsigned int* vtable, const voxinfo& info, const std::string& base_filename) {
+void write_vox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
 	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + ".vox";
 	fprintf(stdout, "[I/O] Writing data in vox format to %s \n", name.c_str());
 	const int kModel = 256;
 	struct Key { int mx, my, mz; bool operator<(const Key& o) const { return mx != o.mx ? mx < o.mx : (my != o.my ? my < o.my : mz < o.mz); } };
 	std::map<Key, std::vector<unsigned char>> models;     // xyzi quadruples
-	const int G = (int)info.gridsize.x;
-	for (int x = 0; x < G; x++)
-		for (int y = 0; y < (int)info.gridsize.z; y++)
-			for (int z = 0; z < (int)info.gridsize.y; z++) {
-				if (!check_voxel(x, y, z, info.gridsize, vtable)) continue;
-				const int vx = x, vy = -z + (int)info.gridsize.z, vz = y;   // the reference's axis mapping
-				auto& m = models[Key{vx / kModel, vy / kModel, vz / kModel}];
-				m.push_back((unsigned char)(vx % kModel)); m.push_back((unsigned char)(vy % kModel)); m.push_back((unsigned char)(vz % kModel)); m.push_back(1);
-			}
+	const uint64_t G = vox.gridsize;
+	for (uint64_t k : traversal_keys(vox, Axis::x, Axis::y, Axis::z)) {
+		const int x = (int)(k / (G * G)), y = (int)((k / G) % G), z = (int)(k % G);
+		const int vx = x, vy = -z + (int)info.gridsize.z, vz = y;       // the reference's axis mapping (util_io.cpp:276)
+		auto& m = models[Key{vx / kModel, vy / kModel, vz / kModel}];
+		m.push_back((unsigned char)(vx % kModel)); m.push_back((unsigned char)(vy % kModel)); m.push_back((unsigned char)(vz % kModel)); m.push_back(1);
+	}
 	std::vector<char> children;
 	for (auto& kv : models) {
 		std::vector<char> size, xyzi;

@@ -167,6 +167,14 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]);
 
+/*
+ * Table consumer (replaces the G^3 host checkVoxel() loops of the writers, src/util_io.cpp:92-285): compacts the set
+ * bits of `table_words` table words into a device array of voxel indices, ascending — linear idx = x + G*y + G*G*z
+ * (or the morton code for a morton table); `first_voxel` is added to every index (the index of a region's first
+ * voxel, 0 for a whole table).  *d_indices is allocated here (voxb200_free it).  Synchronises `stream`.
+ */
+int voxb200_extract_voxels(const unsigned int* d_table, size_t table_words, uint64_t first_voxel, uint64_t** d_indices, size_t* count, void* stream);
+
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Kernels launched by this library since the last reset (the bench's "gpu_launches"). */
 uint64_t voxb200_launch_count(int reset);

@@ -190,6 +190,19 @@ def test_multi_region_routing(vb, solid, morton):
         vb.route_triangles_multi(grid, d_tris, regions, out[:9], solid=bool(solid), morton=bool(morton))   # capacity too small
 
 
+@pytest.mark.parametrize("name,g,solid", [("bunny", 64, 0), ("bunny", 128, 1), ("icosphere:16:64", 100, 0)])
+def test_extract_voxels_matches_table(vb, name, g, solid):
+    """voxb200_extract_voxels (device-side table consumer): ascending indices of exactly the set voxels."""
+    table, grid = _run(vb, name, g, solid, 0)
+    d_table = torch.from_numpy(table.view(np.int32)).cuda()
+    got = vb.extract_voxels(d_table)
+    bits = np.unpackbits(table.view(np.uint8).reshape(-1, 4)[:, ::-1].reshape(-1))      # bit k = voxel index k
+    want = np.nonzero(bits)[0].astype(np.uint64)
+    assert np.array_equal(got, want)
+    assert np.array_equal(vb.extract_voxels(d_table[:1024], first_voxel=5 * 32), want[want < 1024 * 32] + 5 * 32)
+    assert len(vb.extract_voxels(torch.zeros(4096, dtype=torch.int32, device="cuda"))) == 0
+
+
 def test_upload_paths(vb):
     """Triangle upload (main.cpp:61-80 replaced): soup and indexed uploads, AoS and SoA4, plus the
     device bbox reduction, all lead to the same table as torch-owned memory."""
