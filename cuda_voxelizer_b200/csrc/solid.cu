@@ -54,7 +54,7 @@ template <bool SCAN, bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, const float* __restrict__ tris,
                                                            unsigned int* __restrict__ table,
                                                            unsigned long long* __restrict__ counters,
-                                                           uint2* __restrict__ queue) {
+                                                           const QueueView q) {
 	__shared__ __align__(16) float stage[SOA4 ? 4 : kBlock * 9];
 	const unsigned long long block_first = (unsigned long long)blockIdx.x * kBlock;
 	const unsigned long long i = block_first + threadIdx.x;
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, c
 			items = (unsigned int)((samples + kSamplesPerItem - 1) / kSamplesPerItem);
 		}
 	}
-	enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
+	enqueue_warp(live && big, items, (unsigned int)i, q);
 	if (!live || big) return;
 	for (int y = s.y0; y <= s.y1; y++)
 		for (int z = s.z0; z <= s.z1; z++) solid_emit<SCAN, MORTON>(s, g, y, z, table, counters);
@@ -89,20 +89,15 @@ template <bool SCAN, bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, const float* __restrict__ tris,
                                                             unsigned int* __restrict__ table,
                                                             unsigned long long* __restrict__ counters,
-                                                            const uint2* __restrict__ queue) {
-	const unsigned long long packed = counters[kCtrQueue];
+                                                            const QueueView q) {
+	const unsigned long long packed = *q.cursor;
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_items = (unsigned int)packed;
 	const int lane = threadIdx.x & 31;
 	const unsigned int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
 	const unsigned int n_warps = (gridDim.x * kBlock) >> 5;
 	for (unsigned int item = warp; item < n_items; item += n_warps) {
-		unsigned int lo = 0u, hi = n_entries - 1u;
-		while (lo < hi) {
-			const unsigned int mid = (lo + hi + 1u) >> 1;
-			if (__ldg(&queue[mid].y) <= item) lo = mid; else hi = mid - 1u;
-		}
-		const uint2 e = __ldg(&queue[lo]);
+		const uint2 e = __ldg(&q.entries[find_slot(q, item, n_entries, n_items)]);
 		Tri t;
 		if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
 		shift_tri(t, g);
@@ -194,7 +189,7 @@ __global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restr
 template <bool SCAN, bool MORTON, bool SOA4>
 static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_marks, cudaStream_t st) {
 	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
-	solid_tri_kernel<SCAN, MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.queue);
+	solid_tri_kernel<SCAN, MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view());
 	g_launch_count++;
 	prof_mark(ws, 2, st);
 	cudaError_t err = cudaGetLastError();
@@ -203,7 +198,7 @@ static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const flo
 	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<SCAN, MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
-	solid_coop_kernel<SCAN, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.queue);
+	solid_coop_kernel<SCAN, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view());
 	g_launch_count++;
 	return cudaGetLastError();
 }

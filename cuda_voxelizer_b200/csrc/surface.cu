@@ -235,8 +235,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.com
 template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
                                                                 unsigned int* __restrict__ table,
-                                                                unsigned long long* __restrict__ counters,
-                                                                uint2* __restrict__ queue, uint4* __restrict__ setups, unsigned int setup_cap) {
+                                                                const QueueView q) {
 	__shared__ __align__(16) float stage[SOA4 ? 4 : (kTriBlock / 32) * 288];
 	const int lane = threadIdx.x & 31;
 	const unsigned long long tile = ((unsigned long long)blockIdx.x * kTriBlock + threadIdx.x) >> 5;
@@ -282,8 +281,8 @@ __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams
 			items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
 		}
 	}
-	const unsigned int slot = enqueue_warp(live && big, items, (unsigned int)i, counters + kCtrQueue, queue);
-	if (slot < setup_cap) store_setup(setups + (size_t)slot * kSetupVec, s);
+	const unsigned int slot = enqueue_warp(live && big, items, (unsigned int)i, q);
+	if (slot < q.setup_cap) store_setup(q.setups + (size_t)slot * kSetupVec, s);
 	if (!live || big) return;
 	const unsigned int hit = surf_micro3(s, g);
 	if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
@@ -389,9 +388,8 @@ __device__ __forceinline__ void surf_solve_row(const SurfSetup& s, const GridPar
 template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g, const float* __restrict__ tris,
                                                               unsigned int* __restrict__ table,
-                                                              const unsigned long long* __restrict__ counters,
-                                                              const uint2* __restrict__ queue, const uint4* __restrict__ setups, unsigned int setup_cap) {
-	const unsigned long long packed = counters[kCtrQueue];
+                                                              const QueueView q) {
+	const unsigned long long packed = *q.cursor;
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_items = (unsigned int)packed;
 	const int sub = threadIdx.x & (kRowsPerItem - 1);                       // my row within the item
@@ -400,15 +398,11 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 	const bool aligned = (g.G & 31) == 0;
 
 	for (unsigned int item = group; item < n_items; item += n_groups) {
-		unsigned int lo_e = 0u, hi_e = n_entries - 1u;                      // last entry whose first item <= item
-		while (lo_e < hi_e) {
-			const unsigned int mid = (lo_e + hi_e + 1u) >> 1;
-			if (__ldg(&queue[mid].y) <= item) lo_e = mid; else hi_e = mid - 1u;
-		}
-		const uint2 e = __ldg(&queue[lo_e]);
+		const unsigned int lo_e = find_slot(q, item, n_entries, n_items);
+		const uint2 e = __ldg(&q.entries[lo_e]);
 		SurfSetup s;
-		if (lo_e < setup_cap) {
-			load_setup(setups + (size_t)lo_e * kSetupVec, s);       // computed once by the per-triangle kernel
+		if (lo_e < q.setup_cap) {
+			load_setup(q.setups + (size_t)lo_e * kSetupVec, s);       // computed once by the per-triangle kernel
 		} else {
 			Tri t;
 			if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
@@ -451,7 +445,7 @@ template <bool MORTON, bool SOA4>
 static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table, cudaStream_t st) {
 	const unsigned long long tiles = (g.n_tris + 31ull) / 32ull;
 	const unsigned long long blocks = (tiles + (kTriBlock / 32) - 1) / (kTriBlock / 32);
-	surface_tri_kernel<MORTON, SOA4><<<(unsigned)blocks, kTriBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue, ws.setups, (unsigned int)ws.setup_cap);
+	surface_tri_kernel<MORTON, SOA4><<<(unsigned)blocks, kTriBlock, 0, st>>>(g, d_tris, d_table, ws.view());
 	g_launch_count++;
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
@@ -460,7 +454,7 @@ static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* 
 	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
-	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.counters, ws.queue, ws.setups, (unsigned int)ws.setup_cap);
+	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.view());
 	g_launch_count++;
 	return cudaGetLastError();
 }

@@ -230,6 +230,11 @@ cudaError_t ensure_queue(Workspace& ws, size_t entries) {
 		if (cudaMalloc(&ws.setups, want * kSetupVec * sizeof(uint4)) == cudaSuccess) ws.setup_cap = want;
 		else cudaGetLastError();          // optional: without it every slot recomputes
 	}
+	if (!ws.dir) {
+		const size_t dir_entries = size_t(1) << 20;          // covers 64 M work items; items beyond it fall back to the full search
+		if (cudaMalloc(&ws.dir, dir_entries * sizeof(unsigned int)) == cudaSuccess) ws.dir_cap = dir_entries;
+		else cudaGetLastError();
+	}
 	return cudaSuccess;
 }
 cudaError_t ensure_scratch(Workspace& ws, size_t words) {

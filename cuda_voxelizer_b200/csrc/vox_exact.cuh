@@ -381,9 +381,19 @@ __device__ __forceinline__ void load_tri_block_aos(const float* __restrict__ tri
 // Reserves, for every pushing lane of the warp, one queue slot and `items` consecutive work items with a
 // single packed atomicAdd ((slots << 32) | items).  Because both halves advance together, queue[] ends
 // up sorted by first-item, which is what lets the cooperative kernel binary-search item -> triangle.
+// The cooperative-path work queue as the kernels see it.
+struct QueueView {
+	uint2* entries;                 // {triangle, first work item}, sorted by first item (slots and items are reserved together)
+	unsigned long long* cursor;     // packed (entries << 32) | items
+	uint4* setups;                  // stored SurfSetup of slot < setup_cap
+	unsigned int setup_cap;
+	unsigned int* dir;              // dir[b] = slot of the triangle that owns work item 64*b (b < dir_cap): bounds the item -> slot search
+	unsigned int dir_cap;
+};
+constexpr int kDirShift = 6;
+
 // Returns the caller's queue slot (0xffffffff when it did not push).
-__device__ __forceinline__ unsigned int enqueue_warp(bool push, unsigned int items, unsigned int tri,
-                                                     unsigned long long* counter, uint2* __restrict__ queue) {
+__device__ __forceinline__ unsigned int enqueue_warp(bool push, unsigned int items, unsigned int tri, const QueueView& q) {
 	const unsigned int pushers = __ballot_sync(0xffffffffu, push);
 	if (pushers == 0u) return 0xffffffffu;
 	const int lane = threadIdx.x & 31;
@@ -396,12 +406,27 @@ __device__ __forceinline__ unsigned int enqueue_warp(bool push, unsigned int ite
 	}
 	const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
 	unsigned long long base = 0ull;
-	if (lane == 0) base = atomicAdd(counter, ((unsigned long long)__popc(pushers) << 32) | (unsigned long long)total);
+	if (lane == 0) base = atomicAdd(q.cursor, ((unsigned long long)__popc(pushers) << 32) | (unsigned long long)total);
 	base = __shfl_sync(0xffffffffu, base, 0);
 	if (!push) return 0xffffffffu;
 	const unsigned int slot = (unsigned int)(base >> 32) + __popc(pushers & ((1u << lane) - 1u));
-	queue[slot] = make_uint2(tri, (unsigned int)base + (incl - mine));
+	const unsigned int first = (unsigned int)base + (incl - mine);
+	q.entries[slot] = make_uint2(tri, first);
+	// every multiple of 64 inside [first, first + items) gets this slot in the directory
+	for (unsigned int b = (first + (1u << kDirShift) - 1u) >> kDirShift; b < q.dir_cap && (b << kDirShift) < first + items; b++) q.dir[b] = slot;
 	return slot;
+}
+
+// Slot of the queued triangle that owns work item `item` (n_entries, n_items from the cursor).
+__device__ __forceinline__ unsigned int find_slot(const QueueView& q, unsigned int item, unsigned int n_entries, unsigned int n_items) {
+	const unsigned int b = item >> kDirShift;
+	unsigned int lo = b < q.dir_cap ? __ldg(q.dir + b) : 0u;
+	unsigned int hi = (b + 1u < q.dir_cap && ((b + 1u) << kDirShift) < n_items) ? __ldg(q.dir + b + 1u) : n_entries - 1u;
+	while (lo < hi) {                                   // last entry whose first item <= item
+		const unsigned int mid = (lo + hi + 1u) >> 1;
+		if (__ldg(&q.entries[mid].y) <= item) lo = mid; else hi = mid - 1u;
+	}
+	return lo;
 }
 
 }  // namespace voxb

@@ -18,6 +18,14 @@ struct Workspace {
 	size_t queue_cap = 0;                     // entries
 	uint4* setups = nullptr;                  // stored SurfSetup of the first setup_cap queued triangles (kSetupVec x 16 B each)
 	size_t setup_cap = 0;
+	unsigned int* dir = nullptr;              // work-item directory (one slot per 64 items)
+	size_t dir_cap = 0;
+	QueueView view() const {
+		QueueView q;
+		q.entries = queue; q.cursor = counters + 0; q.setups = setups; q.setup_cap = (unsigned int)setup_cap;
+		q.dir = dir; q.dir_cap = (unsigned int)dir_cap;
+		return q;
+	}
 	unsigned int* route_masks = nullptr;      // multi-region routing: per-triangle region mask
 	size_t route_cap = 0;
 	unsigned long long* route_counts = nullptr;   // 32 counters + 32 cursors
