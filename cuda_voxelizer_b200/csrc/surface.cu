@@ -172,6 +172,124 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 	return valid & ~(rej | xy27 | yz27 | zx27);
 }
 
+// The same branch-free evaluation for a bbox of at most 4x4x4 voxels (triangles up to ~3 voxels across, whatever their
+// alignment).  64 candidates: bit (3-i) + 4j + 16k of the result = voxel (x0+i, y0+j, z0+k), built as four 16-bit
+// z-slices.  Used for the whole warp as soon as one of its triangles does not fit 3x3x3.
+__device__ __forceinline__ unsigned long long surf_micro4(const SurfSetup& s, const GridParams& g) {
+	float px[4], py[4], pz[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) {
+		px[i] = fmul((float)(s.x0 + i), g.ux);
+		py[i] = fmul((float)(s.y0 + i), g.uy);
+		pz[i] = fmul((float)(s.z0 + i), g.uz);
+	}
+	float nxp[4], nyp[4], nzp[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
+	unsigned int rej[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+	for (int k = 0; k < 4; k++)
+#pragma unroll
+		for (int j = 3; j >= 0; j--)
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const float sdp = fadd(fadd(nxp[i], nyp[j]), nzp[k]);
+				const float prod = fmul(fadd(sdp, s.d1), fadd(sdp, s.d2));
+				rej[k] = sign_in(rej[k], fsub(0.0f, prod));
+			}
+	unsigned int rxy = 0u, ryz = 0u, rzx = 0u;          // 16 cells each: (i,j) -> (3-i)+4j, (j,k) -> j+4k, (k,i) -> (3-i)+4k
+	{
+		float a[3][4], b[3][4];
+#pragma unroll
+		for (int e = 0; e < 3; e++)
+#pragma unroll
+			for (int i = 0; i < 4; i++) { a[e][i] = fmul(s.xy_a[e], px[i]); b[e][i] = fmul(s.xy_b[e], py[i]); }
+#pragma unroll
+		for (int j = 3; j >= 0; j--)
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const float v0 = fadd(fadd(a[0][i], b[0][j]), s.xy_d[0]);
+				const float v1 = fadd(fadd(a[1][i], b[1][j]), s.xy_d[1]);
+				const float v2 = fadd(fadd(a[2][i], b[2][j]), s.xy_d[2]);
+				rxy = sign_in(rxy, fminf(fminf(v0, v1), v2));
+			}
+	}
+	{
+		float a[3][4], b[3][4];
+#pragma unroll
+		for (int e = 0; e < 3; e++)
+#pragma unroll
+			for (int i = 0; i < 4; i++) { a[e][i] = fmul(s.yz_a[e], py[i]); b[e][i] = fmul(s.yz_b[e], pz[i]); }
+#pragma unroll
+		for (int k = 3; k >= 0; k--)
+#pragma unroll
+			for (int j = 3; j >= 0; j--) {
+				const float v0 = fadd(fadd(a[0][j], b[0][k]), s.yz_d[0]);
+				const float v1 = fadd(fadd(a[1][j], b[1][k]), s.yz_d[1]);
+				const float v2 = fadd(fadd(a[2][j], b[2][k]), s.yz_d[2]);
+				ryz = sign_in(ryz, fminf(fminf(v0, v1), v2));
+			}
+	}
+	{
+		float a[3][4], b[3][4];
+#pragma unroll
+		for (int e = 0; e < 3; e++)
+#pragma unroll
+			for (int i = 0; i < 4; i++) { a[e][i] = fmul(s.zx_a[e], pz[i]); b[e][i] = fmul(s.zx_b[e], px[i]); }
+#pragma unroll
+		for (int k = 3; k >= 0; k--)
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				const float v0 = fadd(fadd(a[0][k], b[0][i]), s.zx_d[0]);
+				const float v1 = fadd(fadd(a[1][k], b[1][i]), s.zx_d[1]);
+				const float v2 = fadd(fadd(a[2][k], b[2][i]), s.zx_d[2]);
+				rzx = sign_in(rzx, fminf(fminf(v0, v1), v2));
+			}
+	}
+	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..3
+	const unsigned int valid_xy = (((0xfu << (3 - ex)) & 0xfu) * 0x1111u) & ((16u << (4 * ey)) - 1u);
+	unsigned long long hit = 0ull;
+#pragma unroll
+	for (int k = 3; k >= 0; k--) {
+		const unsigned int m = (ryz >> (4 * k)) & 0xfu;                                  // row bits j of slice k -> 4 bits each
+		const unsigned int yz16 = ((m & 1u) | ((m & 2u) << 3) | ((m & 4u) << 6) | ((m & 8u) << 9)) * 0xfu;
+		const unsigned int zx16 = ((rzx >> (4 * k)) & 0xfu) * 0x1111u;                   // x bits of slice k, copied to every row
+		const unsigned int h = (k <= ez) ? (valid_xy & ~(rej[k] | rxy | yz16 | zx16)) : 0u;
+		hit = (hit << 16) | (unsigned long long)(h & 0xffffu);
+	}
+	return hit;
+}
+
+// Writes a 64-bit hit mask of surf_micro4 into the table, one (y,z) row — four x-adjacent bits — at a time.
+template <bool MORTON>
+__device__ __forceinline__ void scatter_hits4(unsigned long long hit, int x0, int y0, int z0, const GridParams& g,
+                                              unsigned int* __restrict__ table) {
+	const bool fast = !MORTON && (g.G & 31) == 0 && g.G <= 4096;
+	const unsigned int Gw = (unsigned int)g.G >> 5;
+	const unsigned int w0 = fast ? Gw * ((unsigned int)y0 + (unsigned int)g.G * (unsigned int)z0) + ((unsigned int)x0 >> 5) - (unsigned int)g.word_base : 0u;
+	const unsigned int sh = (unsigned int)x0 & 31u;
+	while (hit) {
+		const int r = (__ffsll((long long)hit) - 1) >> 2;      // row = j + 4k
+		const unsigned int bits = (unsigned int)(hit >> (4 * r)) & 0xfu;        // x0 at bit 3 ... x0+3 at bit 0
+		hit &= ~(0xfull << (4 * r));
+		const int k = r >> 2, j = r & 3;
+		if (fast) {
+			const unsigned int w = w0 + Gw * ((unsigned int)j + (unsigned int)g.G * (unsigned int)k);
+			const unsigned int v = bits << 28;
+			const unsigned int hi = v >> sh, lo = __funnelshift_r(0u, v, sh);
+			if (hi) atomicOr(table + w, hi);
+			if (lo) atomicOr(table + w + 1, lo);
+		} else {
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				if (!((bits >> (3 - i)) & 1u)) continue;
+				const unsigned long long idx = voxel_index<MORTON>(g, x0 + i, y0 + j, z0 + k);
+				atomicOr(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
+			}
+		}
+	}
+}
+
 // Writes a 27-bit hit mask (bit (2-i) + 3j + 9k = voxel (x0+i, y0+j, z0+k)) into the table: one (y,z) row — three
 // x-adjacent bits — at a time, as one atomicOr, or two when the row straddles a word.
 template <bool MORTON>
@@ -271,21 +389,29 @@ __global__ void __launch_bounds__(kTriBlock) surface_tri_kernel(const GridParams
 		live = clip_to_region(g, s);          // triangles of other slabs (multi-GPU regions) stop here
 	}
 	if (!__any_sync(0xffffffffu, live)) return;
+	bool fits3 = false;
 	if (live) {
 		surf_setup_tests(t, g, s);
-		{
-			const int dx = s.x1 - s.x0, dy = s.y1 - s.y0, dz = s.z1 - s.z0;
-			micro = dx <= 2 && dy <= 2 && dz <= 2;
-			const unsigned long long rows = (unsigned long long)(dy + 1) * (unsigned long long)(dz + 1);
-			big = !micro;
-			items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
-		}
+		const int dx = s.x1 - s.x0, dy = s.y1 - s.y0, dz = s.z1 - s.z0;
+		fits3 = dx <= 2 && dy <= 2 && dz <= 2;
+		micro = dx <= 3 && dy <= 3 && dz <= 3;
+		const unsigned long long rows = (unsigned long long)(dy + 1) * (unsigned long long)(dz + 1);
+		big = !micro;
+		items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
 	}
 	const unsigned int slot = enqueue_warp(live && big, items, (unsigned int)i, q);
 	if (slot < q.setup_cap) store_setup(q.setups + (size_t)slot * kSetupVec, s);
-	if (!live || big) return;
-	const unsigned int hit = surf_micro3(s, g);
-	if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
+	const bool mine = live && !big;
+	// one code path per warp: the 64-candidate evaluation as soon as any of its triangles needs it
+	if (__any_sync(0xffffffffu, mine && !fits3)) {
+		if (mine) {
+			const unsigned long long hit = surf_micro4(s, g);
+			if (hit) scatter_hits4<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
+		}
+	} else if (mine) {
+		const unsigned int hit = surf_micro3(s, g);
+		if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
+	}
 }
 
 // ------------------------------------------------------------------------------------------------
