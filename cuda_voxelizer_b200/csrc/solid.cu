@@ -11,9 +11,10 @@
 //
 // Schedule: zero_kernel -> solid_tri_kernel (thread per triangle; triangles with many samples are
 // queued) -> solid_coop_kernel (warp per block of samples of a queued triangle) -> solid_scan_kernel.
-// MARK+SCAN needs a linear table whose rows are whole words (G a power of two >= 32); every other
-// case (morton order, odd grid sizes) takes the DIRECT mode, which flips the run itself, one atomic
-// per touched word.
+// MARK+SCAN needs a linear table whose rows are whole words (G a power of two, 32..4096).  Morton order (whole grid)
+// runs MARK+SCAN in a linear scratch table and permutes it into the morton table (linear_to_morton_kernel).  Every
+// other case (odd grid sizes, morton sub-regions) takes the DIRECT mode, which flips the run itself, one atomic per
+// touched word.
 #include "vox_internal.h"
 
 namespace voxb {
@@ -185,6 +186,40 @@ __global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restr
 	}
 }
 
+// Linear table -> morton table.  A morton word holds a 4(x) x 4(y) x 2(z) brick: in-word index m = x0 + 2 y0 + 4 z0 + 8 x1
+// + 16 y1 (bit 31 - m).  One thread per output word gathers the brick's eight x-nibbles from the linear rows.
+// Used by the solid path in morton order: the column scan needs linear rows, so the fill runs in a linear scratch
+// table and is permuted once, instead of flipping O(G) morton-scattered voxels per column hit.
+__device__ __forceinline__ unsigned int compact3_dev(unsigned long long m) {        // bits 0,3,6,... of m
+	m &= 0x1249249249249249ull;
+	m = (m | (m >> 2)) & 0x10c30c30c30c30c3ull;
+	m = (m | (m >> 4)) & 0x100f00f00f00f00full;
+	m = (m | (m >> 8)) & 0x001f0000ff0000ffull;
+	m = (m | (m >> 16)) & 0x001f00000000ffffull;
+	m = (m | (m >> 32)) & 0x00000000001fffffull;
+	return (unsigned int)m;
+}
+template <bool XOR_INTO>
+__global__ void __launch_bounds__(kBlock) linear_to_morton_kernel(const unsigned int* __restrict__ lin, unsigned int* __restrict__ out,
+                                                                  size_t n_words, int G) {
+	const size_t w = (size_t)blockIdx.x * kBlock + threadIdx.x;
+	if (w >= n_words) return;
+	const unsigned long long code = (unsigned long long)w << 5;                      // morton code of the brick's first voxel
+	const unsigned int X = compact3_dev(code), Y = compact3_dev(code >> 1), Z = compact3_dev(code >> 2);
+	const unsigned int Gw = (unsigned int)G >> 5;
+	unsigned int word = 0u;
+#pragma unroll
+	for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+		for (int dy = 0; dy < 4; dy++) {
+			const size_t at = ((size_t)(Z + dz) * G + (Y + dy)) * Gw + (X >> 5);
+			const unsigned int nib = (__ldg(lin + at) >> (28u - (X & 31u))) & 0xfu;      // x = X..X+3, X at the nibble's MSB
+			const int c = 2 * (dy & 1) + 16 * (dy >> 1) + 4 * dz;
+			word |= ((nib >> 2) << (30 - c)) | ((nib & 3u) << (22 - c));
+		}
+	out[w] = XOR_INTO ? (out[w] ^ word) : word;
+}
+
 // ------------------------------------------------------------------------------------------------
 template <bool SCAN, bool MORTON, bool SOA4>
 static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_marks, cudaStream_t st) {
@@ -222,16 +257,21 @@ static cudaError_t run_scan(const unsigned int* marks, unsigned int* out, size_t
 	return cudaGetLastError();
 }
 
-cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
+cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_tris, unsigned int* d_table,
                          size_t region_words, const LaunchOpts& o, cudaStream_t st) {
+	GridParams g = g_in;
 	cudaError_t err = ensure_queue(ws, (size_t)g.n_tris);
 	if (err != cudaSuccess) return err;
 	const bool pow2 = (g.G & (g.G - 1)) == 0;
 	const bool full_xy = g.rx0 == 0 && g.rx1 == g.G && g.ry0 == 0 && g.ry1 == g.G;
-	const bool scan = !o.morton && pow2 && g.G >= 32 && g.G <= 4096 && full_xy;
+	const bool whole = full_xy && g.rz0 == 0 && g.rz1 == g.G;
+	// MARK+SCAN needs linear rows of whole words.  Morton order gets it too (whole grid): fill a linear scratch table,
+	// then permute it into the morton table.
+	const bool via_linear = o.morton && whole && pow2 && g.G >= 32 && g.G <= 4096;
+	const bool scan = (!o.morton && pow2 && g.G >= 32 && g.G <= 4096 && full_xy) || via_linear;
 	unsigned int* marks = d_table;
-	if (scan && o.accumulate) {
-		// marks must start from zero: stage them in library scratch and XOR the scanned rows into the table
+	if (scan && (o.accumulate || via_linear)) {
+		// marks must start from zero in a linear table: stage them in library scratch
 		err = ensure_scratch(ws, region_words);
 		if (err != cudaSuccess) return err;
 		marks = ws.scratch;
@@ -253,8 +293,19 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris
 		prof_mark(ws, 2, st);
 	}
 	prof_mark(ws, 3, st);
-	if (scan && (g.n_tris != 0 || marks != d_table)) {
-		const int seg = g.G / 32;
+	const int seg = g.G / 32;
+	if (via_linear) {
+		if (g.n_tris != 0) {
+			err = run_scan<false>(marks, marks, region_words, seg, st);
+			if (err != cudaSuccess) return err;
+		}
+		const unsigned int blocks = (unsigned int)((region_words + kBlock - 1) / kBlock);
+		if (o.accumulate) linear_to_morton_kernel<true><<<blocks, kBlock, 0, st>>>(marks, d_table, region_words, g.G);
+		else linear_to_morton_kernel<false><<<blocks, kBlock, 0, st>>>(marks, d_table, region_words, g.G);
+		g_launch_count++;
+		err = cudaGetLastError();
+		if (err != cudaSuccess) return err;
+	} else if (scan && (g.n_tris != 0 || marks != d_table)) {
 		err = (marks != d_table) ? run_scan<true>(marks, d_table, region_words, seg, st) : run_scan<false>(marks, d_table, region_words, seg, st);
 		if (err != cudaSuccess) return err;
 	}

@@ -7,7 +7,8 @@
 //                        exact setup, grid bbox, then
 //                          - bbox <= 3x3x3 ("micro", the regime of meshes tessellated near the voxel size):
 //                            all 27 candidates in branch-free straight-line code -> 27-bit hit mask, written
-//                            one (y,z) row (3 x-adjacent bits) per atomicOr;
+//                            one (y,z) row (3 x-adjacent bits) per atomicOr; bbox <= 4x4x4: the same with 64
+//                            candidates, for the whole warp as soon as one of its triangles needs it;
 //                          - anything bigger: queued for the cooperative kernel ({slot, work items} reserved
 //                            with ONE packed 64-bit atomic per warp).
 //   surface_coop_kernel  persistent grid over work items = (queued triangle, kRowsPerItem consecutive (y,z) rows);
