@@ -1,0 +1,41 @@
+"""Small end-to-end run of every kernel family for compute-sanitizer (memcheck / racecheck):
+    compute-sanitizer --tool memcheck python scripts/sanitize.py"""
+import os, sys, copy
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import cuda_voxelizer_b200 as vb
+import cases, oracle
+vb.init(0)
+for name, g in (("bunny", 64), ("icosphere:64:128", 256), ("soup:mixed:2000:1:64", 64)):
+    v, f = cases.mesh(name)
+    soup = oracle.soup(v, f)
+    d = torch.from_numpy(soup).cuda()
+    grid = vb.grid_from_verts(v, g, len(f))
+    mn, mx, unit = oracle.voxinfo(v, g)
+    for solid in (False, True):
+        if solid and name.startswith("soup"):
+            continue
+        for morton in (False, True):
+            fn = vb.voxelize_solid if solid else vb.voxelize
+            got = fn(grid, d, morton=morton)
+            torch.cuda.synchronize()
+            want = (oracle.solid if solid else oracle.surface)(soup, mn, unit, g, morton)
+            assert np.array_equal(got.cpu().numpy().view(np.uint32), want), (name, solid, morton)
+    t = vb.voxelize(grid, d)
+    idx = vb.extract_voxels(t)
+    assert len(idx) == oracle.popcount(t.cpu().numpy().view(np.uint32))
+    regions = [vb.partition(g, False, p, 4)[0] for p in range(4)]
+    out = torch.empty(2 * d.numel(), device="cuda")
+    counts = vb.route_triangles_multi(grid, d, regions, out)
+    parts, off = [], 0
+    for p in range(4):
+        g2 = copy.copy(grid); g2.n_triangles = counts[p]
+        seg = out[9 * off: 9 * (off + counts[p])] if counts[p] else torch.zeros(9, device="cuda")
+        parts.append(vb.voxelize(g2, seg.contiguous(), region=regions[p]).clone()); off += counts[p]
+    assert torch.equal(torch.cat(parts), t)
+    buf, mn2, mx2 = vb.upload_indexed(v, f, soa4=True)
+    assert torch.equal(vb.voxelize(grid, buf, soa4=True), t)
+    table, _ = vb.voxelize_host_indexed(grid, v, f)
+    assert np.array_equal(table, t.cpu().numpy().view(np.uint32))
+print("sanitize run ok")
