@@ -276,13 +276,10 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 		if (err != cudaSuccess) return err;
 		marks = ws.scratch;
 	}
-	err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
-	if (err != cudaSuccess) return err;
 	prof_mark(ws, 0, st);
-	if (!o.accumulate || marks != d_table) {
-		err = launch_zero(ws, marks, region_words, st);
-		if (err != cudaSuccess) return err;
-	}
+	if (!o.accumulate || marks != d_table) err = launch_zero(ws, marks, region_words, st, true);       // also resets the counters
+	else err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	if (err != cudaSuccess) return err;
 	prof_mark(ws, 1, st);
 	if (g.n_tris != 0) {
 		if (scan) err = o.soa4 ? run_solid_marks<true, false, true>(ws, g, d_tris, marks, st) : run_solid_marks<true, false, false>(ws, g, d_tris, marks, st);

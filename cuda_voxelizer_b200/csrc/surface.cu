@@ -36,27 +36,31 @@ constexpr int kRowsPerItem = 8;    // (y,z) rows per cooperative work item: one 
 unsigned long long g_launch_count = 0;
 
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) zero_kernel(uint4* __restrict__ p, size_t n16) {
+// Both also reset the library's per-call counters (when given), which saves a separate memset node per call.
+__global__ void __launch_bounds__(512) zero_kernel(uint4* __restrict__ p, size_t n16, unsigned long long* __restrict__ counters) {
+	if (counters != nullptr && blockIdx.x == 0 && threadIdx.x < kNumCounters) counters[threadIdx.x] = 0ull;
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
-__global__ void __launch_bounds__(512) zero_words_kernel(unsigned int* __restrict__ p, size_t n) {
+__global__ void __launch_bounds__(512) zero_words_kernel(unsigned int* __restrict__ p, size_t n, unsigned long long* __restrict__ counters) {
+	if (counters != nullptr && blockIdx.x == 0 && threadIdx.x < kNumCounters) counters[threadIdx.x] = 0ull;
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0u;
 }
 
-cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st) {
-	if (words == 0) return cudaSuccess;
+cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st, bool reset_counters) {
+	unsigned long long* counters = reset_counters ? ws.counters : nullptr;
+	if (words == 0) return reset_counters ? cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st) : cudaSuccess;
 	const int sms = ws.sm_count > 0 ? ws.sm_count : 148;
 	if ((reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (words & 3u) == 0) {
 		const size_t n16 = words / 4;
 		size_t blocks = (n16 + 511) / 512;
 		if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
-		zero_kernel<<<(unsigned)blocks, 512, 0, st>>>(reinterpret_cast<uint4*>(p), n16);
+		zero_kernel<<<(unsigned)blocks, 512, 0, st>>>(reinterpret_cast<uint4*>(p), n16, counters);
 	} else {
 		size_t blocks = (words + 511) / 512;
 		if (blocks > (size_t)sms * 16) blocks = (size_t)sms * 16;
-		zero_words_kernel<<<(unsigned)blocks, 512, 0, st>>>(p, words);
+		zero_words_kernel<<<(unsigned)blocks, 512, 0, st>>>(p, words, counters);
 	}
 	g_launch_count++;
 	return cudaGetLastError();
@@ -590,13 +594,10 @@ cudaError_t launch_surface(Workspace& ws, const GridParams& g, const float* d_tr
                            size_t region_words, const LaunchOpts& o, cudaStream_t st) {
 	cudaError_t err = ensure_queue(ws, (size_t)g.n_tris);
 	if (err != cudaSuccess) return err;
-	err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
-	if (err != cudaSuccess) return err;
 	prof_mark(ws, 0, st);
-	if (!o.accumulate) {
-		err = launch_zero(ws, d_table, region_words, st);
-		if (err != cudaSuccess) return err;
-	}
+	if (!o.accumulate) err = launch_zero(ws, d_table, region_words, st, true);       // also resets the counters
+	else err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+	if (err != cudaSuccess) return err;
 	prof_mark(ws, 1, st);
 	if (g.n_tris != 0) {
 		if (o.morton) err = o.soa4 ? run_surface<true, true>(ws, g, d_tris, d_table, st) : run_surface<true, false>(ws, g, d_tris, d_table, st);

@@ -61,7 +61,7 @@ cudaError_t ensure_queue(Workspace& ws, size_t entries);
 cudaError_t ensure_scratch(Workspace& ws, size_t words);
 
 // Zeroes `words` 32-bit words at p (own kernel: 16-byte stores, grid sized to the SM count).
-cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st);
+cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st, bool reset_counters = false);
 
 // The surface path (voxelize.cu:58-238 replaced): [zero] + per-triangle kernel + cooperative kernel.
 cudaError_t launch_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,
