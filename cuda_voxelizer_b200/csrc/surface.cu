@@ -551,9 +551,20 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 		int xa, xb;
 		surf_solve_row(s, g, row, xa, xb);
 		if (xa > xb) continue;
-		if (MORTON || !aligned) {
+		if (MORTON) {
+			// the row in morton order: y and z are spread once, x advances in dilated form (x + 1 on bits 0,3,6,...)
+			const unsigned long long kX = 0x1249249249249249ull;
+			const unsigned long long yz = (spread3((unsigned)y) << 1) | (spread3((unsigned)z) << 2);
+			unsigned long long mx = spread3((unsigned)xa);
 			WordRun<false> run;
-			for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<MORTON>(g, x, y, z));
+			for (int x = xa; x <= xb; x++) {
+				run.add(table, g, mx | yz);
+				mx = ((mx | ~kX) + 1ull) & kX;
+			}
+			run.flush(table);
+		} else if (!aligned) {
+			WordRun<false> run;
+			for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<false>(g, x, y, z));
 			run.flush(table);
 		} else {
 			// rows are whole words: first/last word get partial masks (x at bit 31 - x%32), the middle ones 0xffffffff
