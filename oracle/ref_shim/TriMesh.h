@@ -12,6 +12,8 @@
 #pragma once
 #include <vector>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 
 namespace trimesh {
 
@@ -53,8 +55,38 @@ struct TriMesh {
 		}
 	}
 	static void set_verbose(bool) {}
-	// used only by write_obj_cubes' reorder round trip (util_io.cpp:140-149): inert here
-	static TriMesh* read(const char*) { return new TriMesh(); }
+	// Minimal OBJ reader ("v x y z", "f a b c" with optional /t/n suffixes, polygons fanned) so that the reference's
+	// UNMODIFIED main.cpp can load the test fixture (main.cpp:174).  write_obj_cubes' reorder round trip
+	// (util_io.cpp:140-149) also lands here: it re-reads its own output and writes nothing back.
+	static TriMesh* read(const char* path) {
+		TriMesh* m = new TriMesh();
+		FILE* f = std::fopen(path, "rb");
+		if (!f) return m;
+		char line[1 << 14];
+		while (std::fgets(line, sizeof(line), f)) {
+			if (line[0] == 'v' && (line[1] == ' ' || line[1] == '\t')) {
+				char* q = line + 1;
+				float x = std::strtof(q, &q), y = std::strtof(q, &q), z = std::strtof(q, &q);
+				m->vertices.push_back(point(x, y, z));
+			} else if (line[0] == 'f' && (line[1] == ' ' || line[1] == '\t')) {
+				std::vector<int> idx;
+				char* q = line + 1;
+				for (;;) {
+					while (*q == ' ' || *q == '\t') q++;
+					if (*q == 0 || *q == '\n' || *q == '\r') break;
+					char* e;
+					long v = std::strtol(q, &e, 10);
+					if (e == q) break;
+					idx.push_back(v > 0 ? (int)v - 1 : (int)m->vertices.size() + (int)v);
+					q = e;
+					while (*q && *q != ' ' && *q != '\t' && *q != '\n' && *q != '\r') q++;
+				}
+				for (size_t k = 1; k + 1 < idx.size(); k++) m->faces.push_back(Face(idx[0], idx[k], idx[k + 1]));
+			}
+		}
+		std::fclose(f);
+		return m;
+	}
 	void write(const char*) {}
 };
 
