@@ -20,7 +20,7 @@ EXPORTS = [
     "voxb200_partition", "voxb200_morton_encode", "voxb200_malloc", "voxb200_free", "voxb200_memcpy_d2h",
     "voxb200_upload_soup", "voxb200_upload_indexed", "voxb200_surface", "voxb200_solid", "voxb200_voxelize_host",
     "voxb200_launch_count", "voxb200_last_counters", "voxb200_version", "voxb200_set_profiling", "voxb200_phase_ms",
-    "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels",
+    "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release",
 ]
 
 

@@ -230,3 +230,8 @@ def extract_voxels(table, first_voxel=0, stream=None):
         check(_lib.lib().voxb200_memcpy_d2h(C.c_void_p(host.ctypes.data), C.c_void_p(buf.ptr), n.value * 8, _stream_ptr(stream)))
     buf.close()
     return host
+
+
+def release():
+    """Free everything the library cached for the current device."""
+    check(_lib.lib().voxb200_release())

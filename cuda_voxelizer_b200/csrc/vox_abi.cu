@@ -619,6 +619,29 @@ int voxb200_extract_voxels(const unsigned int* d_table, size_t table_words, uint
 	return VOXB200_OK;
 }
 
+int voxb200_release(void) {
+	int dev = -1;
+	if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) { cudaGetLastError(); return VOXB200_OK; }
+	Workspace& ws = g_ws[dev];
+	HostPath& hp = g_hp[dev];
+	if (ws.device == dev) CU(cudaDeviceSynchronize());
+	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch,
+	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces};
+	for (void* p : dev_ptrs) if (p) cudaFree(p);
+	for (void* p : hp.pinned) if (p) cudaFreeHost(p);
+	if (ws.prof_ev) {
+		for (int i = 0; i < kProfRing; i++) for (int k = 0; k < kProfEvents; k++) cudaEventDestroy(ws.prof_ev[i][k]);
+		delete[] ws.prof_ev;
+	}
+	if (hp.stream) cudaStreamDestroy(hp.stream);
+	for (auto& e : hp.ev) if (e) cudaEventDestroy(e);
+	for (auto& e : hp.buf_free) if (e) cudaEventDestroy(e);
+	ws = Workspace();
+	hp = HostPath();
+	cudaGetLastError();
+	return VOXB200_OK;
+}
+
 uint64_t voxb200_launch_count(int reset) {
 	const uint64_t v = g_launch_count;
 	if (reset) g_launch_count = 0;

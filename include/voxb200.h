@@ -96,6 +96,10 @@ int voxb200_partition(unsigned int gridsize, int morton, int part, int n_parts,
                       voxb200_region* out, size_t* region_bytes);
 uint64_t voxb200_morton_encode(unsigned int x, unsigned int y, unsigned int z);
 
+/* Frees every buffer, stream and event the library cached for the current device (work queue, staging, the persistent
+ * buffers of voxb200_voxelize_host*).  The next call re-creates what it needs.  Synchronises the device. */
+int voxb200_release(void);
+
 /* ---- device memory ------------------------------------------------------------------------- */
 int voxb200_malloc(void** dptr, size_t bytes);
 int voxb200_free(void* dptr);

@@ -312,6 +312,18 @@ def test_fuzz_mixed_sizes_vs_oracle(vb, seed):
         assert np.array_equal(got, want), "solid g=%d: %d differing words" % (g, np.count_nonzero(got ^ want))
 
 
+def test_release_and_reuse(vb):
+    """voxb200_release frees the cached scratch; the next call rebuilds it and gives the same table."""
+    name, g = "bunny", 64
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    a = vb.voxelize(grid, d_tris).clone()
+    vb.voxelize_host_indexed(grid, v, f)
+    vb.release()
+    assert torch.equal(vb.voxelize(grid, d_tris), a)
+    assert torch.equal(vb.voxelize_solid(grid, d_tris), vb.voxelize_solid(grid, d_tris).clone())
+
+
 def test_invalid_arguments_report_einval(vb):
     from cuda_voxelizer_b200 import _lib
     grid = vb.make_grid([0, 0, 0], [1, 1, 1], 48, 1)
