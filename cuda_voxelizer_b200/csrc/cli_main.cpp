@@ -27,6 +27,7 @@ struct Options {
 	Format format = Format::vox;
 	bool force_cpu = false;
 	bool solid = false;
+	std::string from_table;    // test hook: skip the GPU, read a raw linear bit table from this file and only run the writer
 };
 
 void print_help() {
@@ -69,6 +70,8 @@ Options parse(int argc, char* argv[]) {
 			o.force_cpu = true;
 		} else if (a == "-solid") {
 			o.solid = true;
+		} else if (a == "--from-table" && i + 1 < argc) {
+			o.from_table = argv[++i];
 		}
 	}
 	if (!have_file) { printf("[Err] You didn't specify a file using -f (path). This is required. Exiting. \n"); exit(1); }
@@ -116,6 +119,30 @@ int main(int argc, char* argv[]) {
 	printf("[Voxelization] Unit length: x: %f y: %f z: %f\n", info.unit.x, info.unit.y, info.unit.z);
 	const size_t vtable_size = voxb200_table_bytes(opt.gridsize);
 
+	if (!opt.from_table.empty()) {
+		// Writer-only mode (host-side tests without a GPU): the table comes from a file instead of the voxelizer.
+		std::vector<unsigned int> table(vtable_size / 4);
+		FILE* tf = fopen(opt.from_table.c_str(), "rb");
+		if (!tf || fread(table.data(), 1, vtable_size, tf) != vtable_size) { printf("[Err] cannot read %zu table bytes from %s \n", vtable_size, opt.from_table.c_str()); return 1; }
+		fclose(tf);
+		VoxelList list;
+		list.gridsize = opt.gridsize;
+		for (size_t w = 0; w < table.size(); w++)
+			for (unsigned int bits = table[w]; bits;) {
+				const int msb = 31 - __builtin_clz(bits);
+				bits &= ~(1u << msb);
+				list.indices.push_back((uint64_t)w * 32 + (uint64_t)(31 - msb));
+			}
+		printf("\n## FILE OUTPUT \n");
+		switch (opt.format) {
+			case Format::morton: write_binary(table.data(), vtable_size, opt.filename); break;
+			case Format::binvox: write_binvox(list, info, opt.filename); break;
+			case Format::obj_points: write_obj_pointcloud(list, info, opt.filename); break;
+			case Format::obj_cubes: write_obj_cubes(list, info, opt.filename); break;
+			case Format::vox: write_vox(list, info, opt.filename); break;
+		}
+		return 0;
+	}
 	if (opt.force_cpu) {
 		printf("\n## CPU VOXELISATION \n");
 		printf("[Err] -cpu: this build has no CPU voxelization path (it targets B200 GPUs only; the reference's CPU voxelizer is kept as a test oracle, not as a product path). Run without -cpu. \n");
