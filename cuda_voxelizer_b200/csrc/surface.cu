@@ -16,8 +16,9 @@
 //                        otherwise the lane SOLVES the row instead of sweeping it: every remaining test is a
 //                        monotone function of x (rounding, int->float and multiplying/adding a constant all
 //                        preserve order), so the accepted voxels of a row form one interval whose two ends are
-//                        found by bisection on the reference's exact expressions — O(log width) evaluations
-//                        instead of width — and written as whole-word masks.
+//                        found by evaluating the reference's exact expressions at a real-arithmetic estimate
+//                        (bisection when the estimate is off) — O(1)..O(log width) evaluations instead of width —
+//                        and written as whole-word masks.  Setups come from the per-triangle kernel (160 B each).
 //
 // Measured and rejected on B200 (10M-triangle mesh @2048^3, profiles/README.md): a persistent per-triangle grid
 // (static stride or ticket counter: +50 % time, DRAM re-reads double); parking results while the zero-fill
