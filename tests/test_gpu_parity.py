@@ -324,6 +324,24 @@ def test_release_and_reuse(vb):
     assert torch.equal(vb.voxelize_solid(grid, d_tris), vb.voxelize_solid(grid, d_tris).clone())
 
 
+@pytest.mark.parametrize("solid", [0, 1])
+def test_unaligned_buffers_take_the_scalar_paths(vb, solid):
+    """Triangle and table pointers that are only 4-byte aligned (views offset by one element): the 16-byte fast paths
+    (cp.async tile fetch, 16-byte zero-fill, 16-byte scan lanes) must step aside, the table must not change."""
+    name, g = "icosphere:64:128", 256
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    want = fn(grid, d_tris).clone()
+    shifted = torch.empty(d_tris.numel() + 1, device="cuda")
+    shifted[1:] = d_tris.view(-1)
+    guard = torch.full((want.numel() + 2,), 0x5a5a5a5a, dtype=torch.int32, device="cuda")
+    got = fn(grid, shifted[1:], table=guard[1:-1])
+    assert shifted[1:].data_ptr() % 16 == 4 and guard[1:-1].data_ptr() % 16 == 4
+    assert torch.equal(got, want)
+    assert int(guard[0]) == 0x5a5a5a5a and int(guard[-1]) == 0x5a5a5a5a          # nothing written outside the table
+
+
 def test_invalid_arguments_report_einval(vb):
     from cuda_voxelizer_b200 import _lib
     grid = vb.make_grid([0, 0, 0], [1, 1, 1], 48, 1)
