@@ -33,6 +33,17 @@ __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b)
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+// Two independent binary32 additions per instruction (FADD2, sm_100): each half is rounded to nearest exactly like
+// __fadd_rn, so pairing additions changes no result bit.  ONLY additions are paired: ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, whereas it never fuses a scalar FMUL into a
+// packed add — products therefore stay scalar (tests/test_abi.py checks the SASS holds no FFMA2 / FMUL2).
+// A scalar broadcast operand (bc) costs nothing: FADD2 takes `R.F32` as its second source.
+#ifndef VOXB_PACKED
+#define VOXB_PACKED 1
+#endif
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }   // a - b == a + (-b), bit for bit
+__device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
 // host fallbacks of helper_math.h:58-66 (a<b?a:b), and std::max(0.0f,x) (§A-8)
 __device__ __forceinline__ float hmin(float a, float b) { return a < b ? a : b; }
 __device__ __forceinline__ float hmax(float a, float b) { return a > b ? a : b; }
@@ -52,9 +63,17 @@ struct Tri {
 
 // cpu_voxelizer.cpp:40-45 / voxelize.cu:71-73 — the vertex shift, one rounded subtraction per coordinate
 __device__ __forceinline__ void shift_tri(Tri& t, const GridParams& g) {
+#if VOXB_PACKED
+	const float2 bxy = make_float2(g.bx, g.by);
+	const float2 a = fsub2(make_float2(t.v0x, t.v0y), bxy), b = fsub2(make_float2(t.v1x, t.v1y), bxy), c = fsub2(make_float2(t.v2x, t.v2y), bxy);
+	const float2 z01 = fsub2(make_float2(t.v0z, t.v1z), bc(g.bz));
+	t.v0x = a.x; t.v0y = a.y; t.v1x = b.x; t.v1y = b.y; t.v2x = c.x; t.v2y = c.y;
+	t.v0z = z01.x; t.v1z = z01.y; t.v2z = fsub(t.v2z, g.bz);
+#else
 	t.v0x = fsub(t.v0x, g.bx); t.v0y = fsub(t.v0y, g.by); t.v0z = fsub(t.v0z, g.bz);
 	t.v1x = fsub(t.v1x, g.bx); t.v1y = fsub(t.v1y, g.by); t.v1z = fsub(t.v1z, g.bz);
 	t.v2x = fsub(t.v2x, g.bx); t.v2y = fsub(t.v2y, g.by); t.v2z = fsub(t.v2z, g.bz);
+#endif
 }
 
 // normalize(cross(e0, e1)) — cpu_voxelizer.cpp:72 with helper_math.h:1436 (cross), :1325 + :78 (normalize)
@@ -118,6 +137,62 @@ __device__ __forceinline__ void surf_bbox(const Tri& t, const GridParams& g, Sur
 }
 
 // Everything but the bbox: normal, plane offsets, the 9 edge functions.
+#if VOXB_PACKED
+// The nine edge functions at once: products scalar, the 27 additions of the nine d_e as 15 (12 of them FADD2).
+// Edge q = 3*plane + e.  d = ((-dot(n_e, v)) + max(0, ua*n_e.x)) + max(0, ub*n_e.y), left to right as in edge_setup;
+// -1*x is the exact negation of x.
+__device__ __forceinline__ void edge_setup9(const float e_a[9], const float e_b[9], const bool flip[3], const float va[9], const float vb[9],
+                                            const float ua[3], const float ub[3], float na[9], float nb[9], float d[9]) {
+	float m1[9], m2[9], t1[9], t2[9];
+#pragma unroll
+	for (int q = 0; q < 9; q++) {
+		na[q] = fmul(-1.0f, e_a[q]);
+		nb[q] = e_b[q];
+		if (flip[q / 3]) { na[q] = -na[q]; nb[q] = -nb[q]; }
+		m1[q] = fmul(na[q], va[q]); m2[q] = fmul(nb[q], vb[q]);
+		t1[q] = max0(fmul(ua[q / 3], na[q])); t2[q] = max0(fmul(ub[q / 3], nb[q]));
+	}
+#pragma unroll
+	for (int q = 0; q < 8; q += 2) {
+		const float2 dot = fadd2(make_float2(m1[q], m1[q + 1]), make_float2(m2[q], m2[q + 1]));
+		const float2 r = fadd2(fadd2(make_float2(-dot.x, -dot.y), make_float2(t1[q], t1[q + 1])), make_float2(t2[q], t2[q + 1]));
+		d[q] = r.x; d[q + 1] = r.y;
+	}
+	d[8] = fadd(fadd(-fadd(m1[8], m2[8]), t1[8]), t2[8]);
+}
+
+__device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams& g, SurfSetup& s) {
+	// :68-70 edges
+	const float2 v0 = make_float2(t.v0x, t.v0y), v1 = make_float2(t.v1x, t.v1y), v2 = make_float2(t.v2x, t.v2y);
+	const float2 e0 = fsub2(v1, v0), e1 = fsub2(v2, v1), e2 = fsub2(v0, v2);
+	const float2 ez01 = fsub2(make_float2(t.v1z, t.v2z), make_float2(t.v0z, t.v1z));
+	const float e0x = e0.x, e0y = e0.y, e0z = ez01.x, e1x = e1.x, e1y = e1.y, e1z = ez01.y, e2x = e2.x, e2y = e2.y, e2z = fsub(t.v0z, t.v2z);
+	tri_normal(e0x, e0y, e0z, e1x, e1y, e1z, s.nx, s.ny, s.nz);
+	// :83-87 plane offsets
+	float cx = (s.nx > 0.0f) ? g.ux : 0.0f;
+	float cy = (s.ny > 0.0f) ? g.uy : 0.0f;
+	float cz = (s.nz > 0.0f) ? g.uz : 0.0f;
+	s.d1 = dot3(s.nx, s.ny, s.nz, fsub(cx, t.v0x), fsub(cy, t.v0y), fsub(cz, t.v0z));
+	s.d2 = dot3(s.nx, s.ny, s.nz, fsub(fsub(g.ux, cx), t.v0x), fsub(fsub(g.uy, cy), t.v0y), fsub(fsub(g.uz, cz), t.v0z));
+	// :91-101 XY (n_e = (-e.y, e.x), flipped if n.z < 0; offsets pair unit.x/unit.y); :103-113 YZ (n_e = (-e.z, e.y), flipped if
+	// n.x < 0; unit.y/unit.z); :115-125 ZX (n_e = (-e.x, e.z), flipped if n.y < 0).  The reference pairs unit.X with the first
+	// ZX component (the coefficient of p.z) and unit.Z with the second (§A-13): kept verbatim.
+	const float e_a[9] = {e0y, e1y, e2y, e0z, e1z, e2z, e0x, e1x, e2x};
+	const float e_b[9] = {e0x, e1x, e2x, e0y, e1y, e2y, e0z, e1z, e2z};
+	const float va[9] = {t.v0x, t.v1x, t.v2x, t.v0y, t.v1y, t.v2y, t.v0z, t.v1z, t.v2z};
+	const float vb[9] = {t.v0y, t.v1y, t.v2y, t.v0z, t.v1z, t.v2z, t.v0x, t.v1x, t.v2x};
+	const bool flip[3] = {s.nz < 0.0f, s.nx < 0.0f, s.ny < 0.0f};
+	const float ua[3] = {g.ux, g.uy, g.ux}, ub[3] = {g.uy, g.uz, g.uz};
+	float na[9], nb[9], d[9];
+	edge_setup9(e_a, e_b, flip, va, vb, ua, ub, na, nb, d);
+#pragma unroll
+	for (int e = 0; e < 3; e++) {
+		s.xy_a[e] = na[e]; s.xy_b[e] = nb[e]; s.xy_d[e] = d[e];
+		s.yz_a[e] = na[3 + e]; s.yz_b[e] = nb[3 + e]; s.yz_d[e] = d[3 + e];
+		s.zx_a[e] = na[6 + e]; s.zx_b[e] = nb[6 + e]; s.zx_d[e] = d[6 + e];
+	}
+}
+#else
 __device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams& g, SurfSetup& s) {
 	// :68-70 edges
 	float e0x = fsub(t.v1x, t.v0x), e0y = fsub(t.v1y, t.v0y), e0z = fsub(t.v1z, t.v0z);
@@ -145,6 +220,8 @@ __device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams&
 	edge_setup(e1x, e1z, fy, t.v1z, t.v1x, g.ux, g.uz, s.zx_a[1], s.zx_b[1], s.zx_d[1]);
 	edge_setup(e2x, e2z, fy, t.v2z, t.v2x, g.ux, g.uz, s.zx_a[2], s.zx_b[2], s.zx_d[2]);
 }
+
+#endif
 
 __device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, SurfSetup& s) {
 	surf_bbox(t, g, s);
