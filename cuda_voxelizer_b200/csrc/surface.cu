@@ -104,6 +104,11 @@ __device__ __forceinline__ bool clip_to_region(const GridParams& g, SurfSetup& s
 //   * voxel b = (2-i) + 3j + 9k (x0 at the high bit of each 3-bit row, MSB-first like the table) survives iff it is inside the bbox and none of the four masks rejects it.
 // Survivors are written one (y,z) row at a time: the 3 x-bits of a row go out as one or two atomicOr.
 // ------------------------------------------------------------------------------------------------
+// atomicOr whose result is not wanted, as a reduction (ptxas keeps a predicated atomicOr as ATOMG, which makes the warp wait for
+// the returned value at exit)
+__device__ __forceinline__ void red_or(unsigned int* p, unsigned int v) {
+	asm volatile("red.relaxed.gpu.global.or.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {       // mask = (mask << 1) | signbit(v)
 	return __funnelshift_l(__float_as_uint(v), mask, 1);
 }
@@ -557,8 +562,8 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 				if (hi == 0x12345678u) atomicOr(q, hi);
 				if (lo == 0x12345678u) atomicOr(q + 1, lo);
 #else
-				if (hi) atomicOr(q, hi);
-				if (lo) atomicOr(q + 1, lo);
+				if (hi) red_or(q, hi);
+				if (lo) red_or(q + 1, lo);
 #endif
 			}
 #else
@@ -598,18 +603,15 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
 
-template <bool MORTON, bool SOA4>
-__global__ void VOXB_TRI_BOUNDS surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
-                                                                unsigned int* __restrict__ table,
-                                                                const QueueView q) {
-	__shared__ __align__(16) float stage[SOA4 ? 4 : (kTriBlock / 32) * 288];
-	const int lane = threadIdx.x & 31;
-	const unsigned long long tile = ((unsigned long long)blockIdx.x * kTriBlock + threadIdx.x) >> 5;
+// Fetches triangle `lane` of `tile` (32 consecutive triangles): the tile's 1152 bytes come in with 72 x 16-byte cp.async
+// into the warp's shared slab and are read back at stride 9 words (conflict-free); scalar loads for the last,
+// partial tile or an unaligned soup.
+template <bool SOA4>
+__device__ __forceinline__ bool load_tile_tri(const GridParams& g, const float* __restrict__ tris, unsigned long long tile, int lane,
+                                              float* my_stage, Tri& t) {
 	const unsigned long long i = (tile << 5) + lane;
 	const bool valid = i < g.n_tris;
 	const bool vec_ok = !SOA4 && (tile << 5) + 32ull <= g.n_tris && (reinterpret_cast<uintptr_t>(tris) & 15u) == 0;
-	float* my_stage = stage + (SOA4 ? 0 : (threadIdx.x >> 5) * 288);
-	Tri t;
 	if (SOA4) {
 		if (valid) load_tri_soa4(tris, g.n_tris, i, t);
 	} else if (vec_ok) {
@@ -627,6 +629,17 @@ __global__ void VOXB_TRI_BOUNDS surface_tri_kernel(const GridParams g, const flo
 	} else if (valid) {
 		load_tri_aos(tris, i, t);
 	}
+	return valid;
+}
+
+// One warp = one tile of 32 consecutive triangles.
+template <bool MORTON, bool SOA4>
+__device__ __forceinline__ void tri_tile(const GridParams& g, const float* __restrict__ tris, unsigned int* __restrict__ table,
+                                         const QueueView& q, unsigned long long tile, float* my_stage) {
+	const int lane = threadIdx.x & 31;
+	Tri t;
+	const bool valid = load_tile_tri<SOA4>(g, tris, tile, lane, my_stage, t);
+	const unsigned long long i = (tile << 5) + lane;
 
 	SurfSetup s;
 	bool live = false, big = false, micro = false;
@@ -650,23 +663,31 @@ __global__ void VOXB_TRI_BOUNDS surface_tri_kernel(const GridParams g, const flo
 	const unsigned int slot = enqueue_warp(live && big, items, (unsigned int)i, q);
 	if (slot < q.setup_cap) store_setup(q.setups + (size_t)slot * kSetupVec, s);
 	const bool mine = live && !big;
-	// one code path per warp: the 64-candidate evaluation as soon as any of its triangles needs it
-	if (__any_sync(0xffffffffu, mine && !fits3)) {
-		if (mine) {
-			const unsigned long long hit = surf_micro4(s, g);
-			if (hit) scatter_hits4<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
-		}
-	} else {
-		unsigned int hit = 0u;
-		if (mine) hit = surf_micro3(s, g);
-#if VOXB_UNROLLED_SCATTER
-		if (!MORTON && (g.G & 31) == 0 && g.G <= 4096) {
-			if (!mine) { s.x0 = 0; s.y0 = 0; s.z0 = 0; }
-			scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);     // converged: every write is predicated on its own bits
-		} else
-#endif
-		if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
+	const bool wide = __any_sync(0xffffffffu, mine && !fits3);      // one code path per warp: 64 candidates as soon as one triangle needs them
+	unsigned long long hit4 = 0ull;
+	unsigned int hit = 0u;
+	if (wide) { if (mine) hit4 = surf_micro4(s, g); }
+	else if (mine) hit = surf_micro3(s, g);
+	if (wide) {
+		if (hit4) scatter_hits4<MORTON>(hit4, s.x0, s.y0, s.z0, g, table);
+		return;
 	}
+#if VOXB_UNROLLED_SCATTER
+	if (!MORTON && (g.G & 31) == 0 && g.G <= 4096) {
+		if (!mine) { s.x0 = 0; s.y0 = 0; s.z0 = 0; }
+		scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);     // converged: every write is predicated on its own bits
+		return;
+	}
+#endif
+	if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
+}
+
+template <bool MORTON, bool SOA4>
+__global__ void VOXB_TRI_BOUNDS surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
+                                                   unsigned int* __restrict__ table, const QueueView q) {
+	__shared__ __align__(16) float stage[SOA4 ? 4 : (kTriBlock / 32) * 288];
+	const unsigned long long tile = ((unsigned long long)blockIdx.x * kTriBlock + threadIdx.x) >> 5;
+	tri_tile<MORTON, SOA4>(g, tris, table, q, tile, stage + (SOA4 ? 0 : (threadIdx.x >> 5) * 288));
 }
 
 // ------------------------------------------------------------------------------------------------
