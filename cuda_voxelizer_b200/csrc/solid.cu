@@ -11,6 +11,14 @@
 //
 // Schedule: zero_kernel -> solid_tri_kernel (thread per triangle; triangles with many samples are
 // queued) -> solid_coop_kernel (warp per block of samples of a queued triangle) -> solid_scan_kernel.
+//
+// ROW LISTS (linear order, fresh table, 128 <= G <= 2048): the marks of a row do not need the table at all until the
+// fill.  Each accepted sample appends its xmax to a short per-row list (a 32-bit counter + kRowMarks 16-bit slots per
+// (y,z) row, L2-resident: 20 B per row) and solid_fill_kernel builds every row straight from its list — the XOR of the
+// prefix masks [0, xmax] — writing each table byte exactly once: no zero-fill, no cold-DRAM atomics, no read-back.
+// A row with more than kRowMarks crossings puts the surplus marks, as single bits, into a library table that is
+// all-zero between calls; the fill suffix-XORs that row in, and clears it again.  Both side buffers are left zeroed by
+// the fill, so a call costs no memset.
 // MARK+SCAN needs a linear table whose rows are whole words (G a power of two, 32..4096).  Morton order (whole grid)
 // runs MARK+SCAN in a linear scratch table and permutes it into the morton table (linear_to_morton_kernel).  Every
 // other case (odd grid sizes, morton sub-regions) takes the DIRECT mode, which flips the run itself, one atomic per
@@ -22,6 +30,9 @@ namespace voxb {
 constexpr int kBlock = 256;
 constexpr int kSmallSamples = 64;     // (y,z) samples a single thread finishes itself
 constexpr int kSamplesPerItem = 256;  // samples per cooperative work item (8 per lane)
+constexpr int kRowMarks = 8;          // listed marks per (y,z) row (one 16-byte vector of 16-bit xmax values)
+
+enum SolidMode { kDirect = 0, kMarkScan = 1, kRowLists = 2 };
 
 __device__ __forceinline__ bool clip_samples_to_region(const GridParams& g, SolidSetup& s) {
 	s.y0 = max(s.y0, g.ry0); s.y1 = min(s.y1, g.ry1 - 1);
@@ -30,9 +41,9 @@ __device__ __forceinline__ bool clip_samples_to_region(const GridParams& g, Soli
 }
 
 // One centre sample (y,z) of one triangle: accept test, xmax, then mark or flip.
-template <bool SCAN, bool MORTON>
+template <int MODE, bool MORTON>
 __device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams& g, int y, int z,
-                                           unsigned int* __restrict__ table, unsigned long long* __restrict__ counters) {
+                                           unsigned int* __restrict__ table, unsigned long long* __restrict__ counters, const RowLists& rl) {
 	const float py = solid_center(y, g.uy), pz = solid_center(z, g.uz);
 	if (!solid_sample(s, py, pz)) return;
 	int xmax = solid_xmax(s, g, py, pz);
@@ -40,7 +51,16 @@ __device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams
 	// >= G writes out of bounds.  Skip / clamp instead and count the event.
 	if (xmax < 0) { atomicAdd(counters + kCtrSolidClamp, 1ull); return; }
 	if (xmax > g.G - 1) { atomicAdd(counters + kCtrSolidClamp, 1ull); xmax = g.G - 1; }
-	if (SCAN) {
+	if (MODE == kRowLists) {
+		// `table` is the library's overflow table here
+		const unsigned int row = (unsigned int)y + (unsigned int)g.G * (unsigned int)(z - g.rz0);
+		const unsigned int slot = atomicAdd(rl.count + row, 1u);
+		if (slot < (unsigned int)kRowMarks) rl.marks[(size_t)row * kRowMarks + slot] = (unsigned short)xmax;
+		else {
+			const unsigned long long idx = voxel_index<false>(g, xmax, y, z);
+			atomicXor(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
+		}
+	} else if (MODE == kMarkScan) {
 		const unsigned long long idx = voxel_index<false>(g, xmax, y, z);
 		atomicXor(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
 	} else {
@@ -51,11 +71,11 @@ __device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams
 	}
 }
 
-template <bool SCAN, bool MORTON, bool SOA4>
+template <int MODE, bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, const float* __restrict__ tris,
                                                            unsigned int* __restrict__ table,
                                                            unsigned long long* __restrict__ counters,
-                                                           const QueueView q) {
+                                                           const QueueView q, const RowLists rl) {
 	__shared__ __align__(16) float stage[SOA4 ? 4 : kBlock * 9];
 	const unsigned long long block_first = (unsigned long long)blockIdx.x * kBlock;
 	const unsigned long long i = block_first + threadIdx.x;
@@ -83,14 +103,14 @@ __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, c
 	enqueue_warp(live && big, items, (unsigned int)i, q);
 	if (!live || big) return;
 	for (int y = s.y0; y <= s.y1; y++)
-		for (int z = s.z0; z <= s.z1; z++) solid_emit<SCAN, MORTON>(s, g, y, z, table, counters);
+		for (int z = s.z0; z <= s.z1; z++) solid_emit<MODE, MORTON>(s, g, y, z, table, counters, rl);
 }
 
-template <bool SCAN, bool MORTON, bool SOA4>
+template <int MODE, bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, const float* __restrict__ tris,
                                                             unsigned int* __restrict__ table,
                                                             unsigned long long* __restrict__ counters,
-                                                            const QueueView q) {
+                                                            const QueueView q, const RowLists rl) {
 	const unsigned long long packed = *q.cursor;
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_items = (unsigned int)packed;
@@ -111,7 +131,7 @@ __global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, 
 		const long long k1 = min(samples, k0 + (long long)kSamplesPerItem);
 		for (long long k = k0 + lane; k < k1; k += 32) {
 			const int y = s.y0 + (int)(k / nz), z = s.z0 + (int)(k % nz);
-			solid_emit<SCAN, MORTON>(s, g, y, z, table, counters);
+			solid_emit<MODE, MORTON>(s, g, y, z, table, counters, rl);
 		}
 	}
 }
@@ -186,6 +206,77 @@ __global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restr
 	}
 }
 
+// ROW LISTS fill: every table byte written once, from the row's list.  A lane owns 4 consecutive words (one 16-byte
+// store); a row is `lanes_per_row` = G/128 <= 16 consecutive lanes of a warp.  Word wi of a row whose marks are m_1..m_n:
+// XOR over the marks of { all ones if wi < m/32; the bits of x = 32 wi .. m (MSB-first) if wi == m/32; 0 otherwise }.
+// Rows that overflowed their list (count > kRowMarks) add the suffix-XOR of their row of the overflow table, which is
+// cleared again on the way.  Counters are reset for the next call.
+constexpr int kFillUnroll = 4;
+__global__ void __launch_bounds__(kBlock) solid_fill_kernel(uint4* __restrict__ out, size_t n_vec, int row_shift, const RowLists rl,
+                                                            uint4* __restrict__ overflow) {
+	const int lane = threadIdx.x & 31;
+	const int width = 1 << row_shift;                             // lanes per row
+	const int pos = lane & (width - 1);
+	// a warp owns kFillUnroll consecutive 32-lane spans; all their loads are issued before any is used
+	const size_t span0 = (((size_t)blockIdx.x * kBlock + threadIdx.x) >> 5) * (size_t)kFillUnroll;
+	unsigned int cnt[kFillUnroll];
+	uint4 mk[kFillUnroll];
+#pragma unroll
+	for (int u = 0; u < kFillUnroll; u++) {
+		// both loads are independent (slots beyond the count hold stale values that are never looked at)
+		const size_t at = (span0 + u) * 32 + lane;
+		cnt[u] = at < n_vec ? rl.count[at >> row_shift] : 0u;
+		mk[u] = at < n_vec ? __ldg(reinterpret_cast<const uint4*>(rl.marks) + (at >> row_shift)) : make_uint4(0u, 0u, 0u, 0u);
+	}
+#pragma unroll
+	for (int u = 0; u < kFillUnroll; u++) {
+		const size_t at = (span0 + u) * 32 + lane;
+		const bool valid = at < n_vec;
+		const unsigned int c = cnt[u];
+		unsigned int w[4] = {0u, 0u, 0u, 0u};
+		const int n = (int)min(c, (unsigned int)kRowMarks);
+		const int nmax = __reduce_max_sync(0xffffffffu, n);
+#pragma unroll
+		for (int i = 0; i < kRowMarks; i++) {
+			if (i < nmax) {                                           // warp-uniform
+				const unsigned int pair = i < 4 ? (i < 2 ? mk[u].x : mk[u].y) : (i < 6 ? mk[u].z : mk[u].w);
+				const unsigned int m = (i & 1) ? (pair >> 16) : (pair & 0xffffu);
+				const int d = i < n ? (int)(m >> 5) - 4 * pos : -1;     // the mark's word, relative to this lane's first (-1: no mark)
+				const unsigned int part = 0xffffffffu << (31u - (m & 31u));
+#pragma unroll
+				for (int j = 0; j < 4; j++) w[j] ^= d > j ? 0xffffffffu : (d == j ? part : 0u);
+			}
+		}
+		if (__any_sync(0xffffffffu, c > (unsigned int)kRowMarks)) {
+			// surplus marks of overflowed rows: suffix-XOR of their overflow-table row (the other rows of the warp contribute zeros)
+			const bool ovf = c > (unsigned int)kRowMarks;
+			const uint4 o = ovf ? overflow[at] : make_uint4(0u, 0u, 0u, 0u);
+			unsigned int s[4] = {o.x, o.y, o.z, o.w};
+			const unsigned int par = (__popc(s[0]) + __popc(s[1]) + __popc(s[2]) + __popc(s[3])) & 1u;
+			unsigned int suf = par;
+#pragma unroll
+			for (int d = 1; d < 32; d <<= 1) {
+				const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
+				if (d < width && pos + d < width) suf ^= dn;
+			}
+			unsigned int carry = suf ^ par;
+#pragma unroll
+			for (int j = 3; j >= 0; j--) {
+				unsigned int v = s[j];
+				v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
+				if (carry) v = ~v;
+				carry ^= __popc(s[j]) & 1u;
+				w[j] ^= v;
+			}
+			if (ovf) overflow[at] = make_uint4(0u, 0u, 0u, 0u);
+		}
+		if (valid) {
+			out[at] = make_uint4(w[0], w[1], w[2], w[3]);
+			if (pos == 0 && c != 0u) rl.count[at >> row_shift] = 0u;
+		}
+	}
+}
+
 // Linear table -> morton table.  A morton word holds a 4(x) x 4(y) x 2(z) brick: in-word index m = x0 + 2 y0 + 4 z0 + 8 x1
 // + 16 y1 (bit 31 - m).  One thread per output word gathers the brick's eight x-nibbles from the linear rows.
 // Used by the solid path in morton order: the column scan needs linear rows, so the fill runs in a linear scratch
@@ -221,19 +312,21 @@ __global__ void __launch_bounds__(kBlock) linear_to_morton_kernel(const unsigned
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool SCAN, bool MORTON, bool SOA4>
+template <int MODE, bool MORTON, bool SOA4>
 static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_marks, cudaStream_t st) {
 	const unsigned int blocks = (unsigned int)((g.n_tris + kBlock - 1) / kBlock);
-	solid_tri_kernel<SCAN, MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view());
+	RowLists rl;
+	rl.count = ws.row_count; rl.marks = ws.row_marks;
+	solid_tri_kernel<MODE, MORTON, SOA4><<<blocks, kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view(), rl);
 	g_launch_count++;
 	prof_mark(ws, 2, st);
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
 	static int per_sm = 0;
-	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<SCAN, MORTON, SOA4>, kBlock, 0);
+	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<MODE, MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
-	solid_coop_kernel<SCAN, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view());
+	solid_coop_kernel<MODE, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view(), rl);
 	g_launch_count++;
 	return cudaGetLastError();
 }
@@ -269,12 +362,46 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 	// then permute it into the morton table.
 	const bool via_linear = o.morton && whole && pow2 && g.G >= 32 && g.G <= 4096;
 	const bool scan = (!o.morton && pow2 && g.G >= 32 && g.G <= 4096 && full_xy) || via_linear;
+	// ROW LISTS: linear order into a fresh table whose rows are 1..16 lanes of 16 bytes
+	const bool lists = scan && !via_linear && !o.accumulate && g.G >= 128 && g.G <= 2048 && (region_words & 3u) == 0 &&
+	                   (reinterpret_cast<uintptr_t>(d_table) & 15u) == 0 && region_words / (size_t)(g.G / 32) <= 0xffffffffull;
+	if (lists) {
+		const size_t n_rows = region_words / (size_t)(g.G / 32);
+		err = ensure_row_lists(ws, n_rows, region_words, st);
+		if (err != cudaSuccess) return err;
+		prof_mark(ws, 0, st);
+		err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
+		if (err != cudaSuccess) return err;
+		prof_mark(ws, 1, st);
+		if (g.n_tris != 0) {
+			err = o.soa4 ? run_solid_marks<kRowLists, false, true>(ws, g, d_tris, ws.scratch, st) : run_solid_marks<kRowLists, false, false>(ws, g, d_tris, ws.scratch, st);
+			if (err != cudaSuccess) return err;
+		} else {
+			prof_mark(ws, 2, st);
+		}
+		prof_mark(ws, 3, st);
+		RowLists rl;
+		rl.count = ws.row_count; rl.marks = ws.row_marks;
+		const size_t n_vec = region_words / 4;
+		int row_shift = 0;
+		while ((128 << row_shift) < g.G) row_shift++;                 // lanes (of 16 bytes) per row = G / 128 = 2^row_shift
+		const size_t fill_threads = (((n_vec + 31) / 32 + kFillUnroll - 1) / kFillUnroll) * 32;
+		solid_fill_kernel<<<(unsigned int)((fill_threads + kBlock - 1) / kBlock), kBlock, 0, st>>>(reinterpret_cast<uint4*>(d_table), n_vec, row_shift, rl,
+		                                                                                         reinterpret_cast<uint4*>(ws.scratch));
+		g_launch_count++;
+		err = cudaGetLastError();
+		if (err != cudaSuccess) return err;
+		prof_mark(ws, 4, st);
+		if (ws.prof_on) ws.prof_calls++;
+		return cudaSuccess;
+	}
 	unsigned int* marks = d_table;
 	if (scan && (o.accumulate || via_linear)) {
 		// marks must start from zero in a linear table: stage them in library scratch
 		err = ensure_scratch(ws, region_words);
 		if (err != cudaSuccess) return err;
 		marks = ws.scratch;
+		ws.scratch_zero = false;          // the row-list path re-clears it before relying on it
 	}
 	prof_mark(ws, 0, st);
 	if (!o.accumulate || marks != d_table) err = launch_zero(ws, marks, region_words, st, true);       // also resets the counters
@@ -282,9 +409,9 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 	if (err != cudaSuccess) return err;
 	prof_mark(ws, 1, st);
 	if (g.n_tris != 0) {
-		if (scan) err = o.soa4 ? run_solid_marks<true, false, true>(ws, g, d_tris, marks, st) : run_solid_marks<true, false, false>(ws, g, d_tris, marks, st);
-		else if (o.morton) err = o.soa4 ? run_solid_marks<false, true, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, true, false>(ws, g, d_tris, d_table, st);
-		else err = o.soa4 ? run_solid_marks<false, false, true>(ws, g, d_tris, d_table, st) : run_solid_marks<false, false, false>(ws, g, d_tris, d_table, st);
+		if (scan) err = o.soa4 ? run_solid_marks<kMarkScan, false, true>(ws, g, d_tris, marks, st) : run_solid_marks<kMarkScan, false, false>(ws, g, d_tris, marks, st);
+		else if (o.morton) err = o.soa4 ? run_solid_marks<kDirect, true, true>(ws, g, d_tris, d_table, st) : run_solid_marks<kDirect, true, false>(ws, g, d_tris, d_table, st);
+		else err = o.soa4 ? run_solid_marks<kDirect, false, true>(ws, g, d_tris, d_table, st) : run_solid_marks<kDirect, false, false>(ws, g, d_tris, d_table, st);
 		if (err != cudaSuccess) return err;
 	} else {
 		prof_mark(ws, 2, st);

@@ -237,10 +237,28 @@ cudaError_t ensure_queue(Workspace& ws, size_t entries) {
 	}
 	return cudaSuccess;
 }
+cudaError_t ensure_row_lists(Workspace& ws, size_t n_rows, size_t words, cudaStream_t st) {
+	cudaError_t e = ensure_scratch(ws, words);
+	if (e != cudaSuccess) return e;
+	if (!ws.scratch_zero) {
+		e = launch_zero(ws, ws.scratch, ws.scratch_words, st);
+		if (e != cudaSuccess) return e;
+		ws.scratch_zero = true;
+	}
+	if (n_rows <= ws.row_cap) return cudaSuccess;
+	if (ws.row_count) cudaFree(ws.row_count);
+	if (ws.row_marks) cudaFree(ws.row_marks);
+	ws.row_count = nullptr; ws.row_marks = nullptr; ws.row_cap = 0;
+	e = cudaMalloc(&ws.row_count, n_rows * sizeof(unsigned int));
+	if (e == cudaSuccess) e = cudaMalloc(&ws.row_marks, n_rows * 8 * sizeof(unsigned short));
+	if (e == cudaSuccess) e = cudaMemsetAsync(ws.row_count, 0, n_rows * sizeof(unsigned int), st);
+	if (e == cudaSuccess) ws.row_cap = n_rows;
+	return e;
+}
 cudaError_t ensure_scratch(Workspace& ws, size_t words) {
 	if (words <= ws.scratch_words) return cudaSuccess;
 	if (ws.scratch) cudaFree(ws.scratch);
-	ws.scratch = nullptr; ws.scratch_words = 0;
+	ws.scratch = nullptr; ws.scratch_words = 0; ws.scratch_zero = false;
 	cudaError_t e = cudaMalloc(&ws.scratch, words * sizeof(unsigned int));
 	if (e == cudaSuccess) ws.scratch_words = words;
 	return e;
@@ -625,7 +643,7 @@ int voxb200_release(void) {
 	Workspace& ws = g_ws[dev];
 	HostPath& hp = g_hp[dev];
 	if (ws.device == dev) CU(cudaDeviceSynchronize());
-	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch,
+	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch, ws.row_count, ws.row_marks,
 	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces};
 	for (void* p : dev_ptrs) if (p) cudaFree(p);
 	for (void* p : hp.pinned) if (p) cudaFreeHost(p);

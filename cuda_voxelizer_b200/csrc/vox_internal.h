@@ -29,8 +29,12 @@ struct Workspace {
 	unsigned int* route_masks = nullptr;      // multi-region routing: per-triangle region mask
 	size_t route_cap = 0;
 	unsigned long long* route_counts = nullptr;   // 32 counters + 32 cursors
-	unsigned int* scratch = nullptr;          // solid: mark table for ACCUMULATE / morton modes
+	unsigned int* scratch = nullptr;          // solid: mark table for ACCUMULATE / morton modes; overflow table of the row-list mode
 	size_t scratch_words = 0;
+	bool scratch_zero = false;                // scratch is all-zero (the row-list mode keeps it so between calls)
+	unsigned int* row_count = nullptr;        // solid row lists: marks per (y,z) row (all-zero between calls) ...
+	unsigned short* row_marks = nullptr;      // ... and kRowMarks 16-bit xmax slots per row
+	size_t row_cap = 0;                       // rows
 	// optional per-phase timing (voxb200_set_profiling): a ring of event sets, one set per call
 	bool prof_on = false;
 	unsigned int prof_calls = 0;
@@ -59,6 +63,14 @@ extern unsigned long long g_launch_count;   // kernels launched by this library 
 
 cudaError_t ensure_queue(Workspace& ws, size_t entries);
 cudaError_t ensure_scratch(Workspace& ws, size_t words);
+// Row-list buffers for n_rows rows plus a ZEROED scratch (overflow) table of `words` words.
+cudaError_t ensure_row_lists(Workspace& ws, size_t n_rows, size_t words, cudaStream_t st);
+
+// Per-row mark lists of the solid path (solid.cu)
+struct RowLists {
+	unsigned int* count;
+	unsigned short* marks;
+};
 
 // Zeroes `words` 32-bit words at p (own kernel: 16-byte stores, grid sized to the SM count).
 cudaError_t launch_zero(Workspace& ws, unsigned int* p, size_t words, cudaStream_t st, bool reset_counters = false);

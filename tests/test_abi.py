@@ -149,3 +149,17 @@ def test_product_never_imports_the_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or fn == "Makefile":
                 src = open(os.path.join(dirpath, fn), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src and "libvoxref" not in src, fn
+
+
+def test_no_contracted_packed_arithmetic_in_sass():
+    """The per-triangle kernels pair additions into FADD2 (two rounded binary32 adds per instruction).  ptxas 12.9
+    contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, which would change results, so products
+    must stay scalar: the library's SASS may hold FADD2 but never FFMA2 / FMUL2."""
+    import shutil
+    import subprocess
+    from cuda_voxelizer_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True, check=True).stdout
+    assert " FADD2 " in sass
+    assert " FFMA2 " not in sass and " FMUL2 " not in sass
