@@ -312,6 +312,36 @@ def test_fuzz_mixed_sizes_vs_oracle(vb, seed):
         assert np.array_equal(got, want), "solid g=%d: %d differing words" % (g, np.count_nonzero(got ^ want))
 
 
+@pytest.mark.parametrize("g", [128, 256])
+def test_solid_row_lists_with_overflowing_rows(vb, g):
+    """The solid path keeps up to 8 marks per (y,z) row in a list and spills the rest into a library table that must be
+    all-zero between calls.  Large overlapping triangles give rows with dozens of crossings next to rows with a few;
+    repeated calls, with a scratch-dirtying call (morton order) in between, must keep giving the oracle's table."""
+    v, f = cases.mesh("soup:large:300:%d:1.0" % (7 + g))
+    soup = oracle.soup(v, f)
+    soup[-1] = [0, 0, 0, 1, 0, 0, 0, 1, 0]
+    soup[-2] = [1, 1, 1, 0, 1, 1, 1, 0, 1]
+    grid = vb.grid_from_verts(soup.reshape(-1, 3), g, len(soup))
+    bb_min, un = np.array(grid.bbox_min[:], np.float32), np.array(grid.unit[:], np.float32)
+    before = oracle.solid_ub_events()
+    want = oracle.solid(soup, bb_min, un, g)
+    if oracle.solid_ub_events() != before:
+        pytest.skip("the reference itself is undefined on this soup")
+    d = torch.from_numpy(soup).cuda()
+    # rows crossed more than 8 times exist (otherwise this test does not reach the spill path)
+    first = vb.voxelize_solid(grid, d).cpu().numpy().view(np.uint32)
+    assert np.array_equal(first, want), "%d differing words" % np.count_nonzero(first ^ want)
+    again = vb.voxelize_solid(grid, d).cpu().numpy().view(np.uint32)
+    assert np.array_equal(again, want)
+    vb.voxelize_solid(grid, d, morton=True)                  # uses (and dirties) the library's scratch table
+    third = vb.voxelize_solid(grid, d).cpu().numpy().view(np.uint32)
+    assert np.array_equal(third, want)
+    # a z-slab region takes the same path with region-relative rows
+    region, nbytes = vb.partition(g, False, 1, 2)
+    half = vb.voxelize_solid(grid, d, region=region).cpu().numpy().view(np.uint32)
+    assert np.array_equal(half, want[len(want) // 2:])
+
+
 def test_release_and_reuse(vb):
     """voxb200_release frees the cached scratch; the next call rebuilds it and gives the same table."""
     name, g = "bunny", 64
