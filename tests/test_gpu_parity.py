@@ -342,6 +342,28 @@ def test_solid_row_lists_with_overflowing_rows(vb, g):
     assert np.array_equal(half, want[len(want) // 2:])
 
 
+@pytest.mark.parametrize("solid", [0, 1])
+def test_cuda_graph_capture_and_replay(vb, solid):
+    """voxb200_surface / voxb200_solid only enqueue work on the caller's stream (no synchronisation, no allocation once
+    the library's scratch exists), so a whole voxelization can be captured into a CUDA graph and replayed — the
+    per-frame use the reference README pitches.  Every replay must reproduce the directly computed table."""
+    name, g = "bunny", 256
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    fn = vb.voxelize_solid if solid else vb.voxelize
+    want = fn(grid, d_tris).clone()                     # also the warm-up that sizes the library's scratch buffers
+    torch.cuda.synchronize()
+    table = torch.empty_like(want)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn(grid, d_tris, table=table)
+    for _ in range(3):
+        table.fill_(-1)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(table, want)
+
+
 def test_release_and_reuse(vb):
     """voxb200_release frees the cached scratch; the next call rebuilds it and gives the same table."""
     name, g = "bunny", 64
