@@ -342,6 +342,10 @@ def run_ours(args):
     names = ["zero_kernel", "surface_tri_kernel" if not solid else "solid_tri_kernel",
              "surface_coop_kernel" if not solid else "solid_coop_kernel", "solid_scan_kernel"]
     alg_bytes = [slab_bytes, tri_bytes, 0, 2 * slab_bytes if solid else 0]
+    if solid and counters.get("solid_row_lists"):
+        # row-list schedule: no zero-fill (phase 0 is the 64-byte counter reset), the fill writes every table byte once
+        names[0], names[3] = "counter_reset", "solid_fill_kernel"
+        alg_bytes[0], alg_bytes[3] = 0, slab_bytes
     dom = int(np.argmax(phases))
     dom_ms = float(phases[dom])
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

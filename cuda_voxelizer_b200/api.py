@@ -163,7 +163,7 @@ def launch_count(reset=False):
 def last_counters():
     out = (C.c_uint64 * 4)()
     check(_lib.lib().voxb200_last_counters(out))
-    return {"coop_triangles": int(out[0]), "coop_items": int(out[1]), "solid_clamped": int(out[2])}
+    return {"coop_triangles": int(out[0]), "coop_items": int(out[1]), "solid_clamped": int(out[2]), "solid_row_lists": int(out[3])}
 
 
 def set_profiling(on):

@@ -365,6 +365,7 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 	// ROW LISTS: linear order into a fresh table whose rows are 1..16 lanes of 16 bytes
 	const bool lists = scan && !via_linear && !o.accumulate && g.G >= 128 && g.G <= 2048 && (region_words & 3u) == 0 &&
 	                   (reinterpret_cast<uintptr_t>(d_table) & 15u) == 0 && region_words / (size_t)(g.G / 32) <= 0xffffffffull;
+	ws.last_row_lists = lists;
 	if (lists) {
 		const size_t n_rows = region_words / (size_t)(g.G / 32);
 		err = ensure_row_lists(ws, n_rows, region_words, st);

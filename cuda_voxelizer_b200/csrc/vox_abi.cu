@@ -702,7 +702,7 @@ int voxb200_last_counters(uint64_t out[4]) {
 	out[0] = c[kCtrQueue] >> 32;
 	out[1] = c[kCtrQueue] & 0xffffffffull;
 	out[2] = c[kCtrSolidClamp];
-	out[3] = 0;
+	out[3] = ws->last_row_lists ? 1 : 0;
 	return VOXB200_OK;
 }
 

@@ -35,6 +35,7 @@ struct Workspace {
 	unsigned int* row_count = nullptr;        // solid row lists: marks per (y,z) row (all-zero between calls) ...
 	unsigned short* row_marks = nullptr;      // ... and kRowMarks 16-bit xmax slots per row
 	size_t row_cap = 0;                       // rows
+	bool last_row_lists = false;              // the last solid call took the row-list schedule (voxb200_last_counters()[3])
 	// optional per-phase timing (voxb200_set_profiling): a ring of event sets, one set per call
 	bool prof_on = false;
 	unsigned int prof_calls = 0;

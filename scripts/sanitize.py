@@ -38,4 +38,14 @@ for name, g in (("bunny", 64), ("icosphere:64:128", 256), ("soup:mixed:2000:1:64
     assert torch.equal(vb.voxelize(grid, buf, soa4=True), t)
     table, _ = vb.voxelize_host_indexed(grid, v, f)
     assert np.array_equal(table, t.cpu().numpy().view(np.uint32))
+# solid rows with more crossings than list slots (the spill path of the row-list schedule), twice in a row
+v, f = cases.mesh("soup:large:300:135:1.0")
+soup = oracle.soup(v, f)
+soup[-1] = [0, 0, 0, 1, 0, 0, 0, 1, 0]; soup[-2] = [1, 1, 1, 0, 1, 1, 1, 0, 1]
+grid = vb.grid_from_verts(soup.reshape(-1, 3), 128, len(soup))
+want = oracle.solid(soup, np.array(grid.bbox_min[:], np.float32), np.array(grid.unit[:], np.float32), 128)
+d = torch.from_numpy(soup).cuda()
+for _ in range(2):
+    assert np.array_equal(vb.voxelize_solid(grid, d).cpu().numpy().view(np.uint32), want)
+assert vb.last_counters()["solid_row_lists"] == 1
 print("sanitize run ok")
