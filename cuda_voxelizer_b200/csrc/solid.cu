@@ -241,10 +241,15 @@ __global__ void __launch_bounds__(kBlock) solid_fill_kernel(uint4* __restrict__ 
 			if (i < nmax) {                                           // warp-uniform
 				const unsigned int pair = i < 4 ? (i < 2 ? mk[u].x : mk[u].y) : (i < 6 ? mk[u].z : mk[u].w);
 				const unsigned int m = (i & 1) ? (pair >> 16) : (pair & 0xffffu);
-				const int d = i < n ? (int)(m >> 5) - 4 * pos : -1;     // the mark's word, relative to this lane's first (-1: no mark)
-				const unsigned int part = 0xffffffffu << (31u - (m & 31u));
+				// word j of this lane holds x = 128 pos + 32 j + (0..31), MSB first; the mark covers its first rel + 1 bits,
+				// rel = m - (128 pos + 32 j): an arithmetic right shift of the top bit by min(rel, 31), nothing for rel < 0
+				const int t = i < n ? (int)m - 128 * pos : -1;
 #pragma unroll
-				for (int j = 0; j < 4; j++) w[j] ^= d > j ? 0xffffffffu : (d == j ? part : 0u);
+				for (int j = 0; j < 4; j++) {
+					const int rel = t - 32 * j;
+					const unsigned int v = (unsigned int)((int)0x80000000 >> min(rel, 31));   // compiles to one clamped SHF
+					w[j] ^= rel >= 0 ? v : 0u;
+				}
 			}
 		}
 		if (__any_sync(0xffffffffu, c > (unsigned int)kRowMarks)) {
