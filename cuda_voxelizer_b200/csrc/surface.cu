@@ -32,7 +32,7 @@ namespace voxb {
 
 constexpr int kBlock = 256;        // cooperative kernel
 constexpr int kTriBlock = 128;     // per-triangle kernel: 4 warps, each with its own staging slab
-constexpr int kRowsPerItem = 8;
+constexpr int kRowsPerItem = 8;    // (y,z) rows per cooperative work item: one per lane of an 8-lane group
 #ifndef VOXB_TRI_MINBLOCKS
 #define VOXB_TRI_MINBLOCKS 6       // per-triangle kernel: 6 blocks of 128 per SM (<= 80 registers)
 #endif
@@ -49,7 +49,7 @@ constexpr int kRowsPerItem = 8;
 #define VOXB_TRI_BOUNDS __launch_bounds__(kTriBlock, VOXB_TRI_MINBLOCKS)
 #else
 #define VOXB_TRI_BOUNDS __launch_bounds__(kTriBlock)
-#endif    // (y,z) rows per cooperative work item: one per lane of an 8-lane group
+#endif
 
 unsigned long long g_launch_count = 0;
 
