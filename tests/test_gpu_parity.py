@@ -252,6 +252,12 @@ def test_empty_and_degenerate_inputs(vb):
     got = vb.voxelize(grid, torch.from_numpy(soup).cuda()).cpu().numpy().view(np.uint32)
     want = oracle.surface(soup, np.array(grid.bbox_min[:], np.float32), np.array(grid.unit[:], np.float32), g)
     assert np.array_equal(got, want)
+    # an empty mesh through every solid schedule (mark+scan at 64, row lists at 128/256) into a dirty table: all zero afterwards
+    for gs in (64, 128, 256):
+        grid = vb.make_grid([0, 0, 0], [1, 1, 1], gs, 0)
+        dirty = torch.full((vb.table_bytes(gs) // 4,), -1, dtype=torch.int32, device="cuda")
+        t = vb.voxelize_solid(grid, torch.zeros(9, device="cuda"), table=dirty)
+        assert int(t.abs().sum()) == 0
 
 
 @pytest.mark.parametrize("g", [32, 64, 256])
