@@ -11,7 +11,7 @@
 //                            candidates, for the whole warp as soon as one of its triangles needs it;
 //                          - anything bigger: queued for the cooperative kernel ({slot, work items} reserved
 //                            with ONE packed 64-bit atomic per warp).
-//   surface_coop_kernel  persistent grid over work items = (queued triangle, kRowsPerItem consecutive (y,z) rows);
+//   surface_coop_kernel  persistent grid over the queued (y,z) rows, 64 consecutive rows per warp and iteration;
 //                        8 lanes per item, ONE LANE PER ROW.  A row failing the x-independent YZ tests is dropped;
 //                        otherwise the lane SOLVES the row instead of sweeping it: every remaining test is a
 //                        monotone function of x (rounding, int->float and multiplying/adding a constant all
@@ -32,7 +32,7 @@ namespace voxb {
 
 constexpr int kBlock = 256;        // cooperative kernel
 constexpr int kTriBlock = 128;     // per-triangle kernel: 4 warps, each with its own staging slab
-constexpr int kRowsPerItem = 8;    // (y,z) rows per cooperative work item: one per lane of an 8-lane group
+constexpr int kRowsPerWarp = 64;   // consecutive queued (y,z) rows one warp of the cooperative kernel takes per iteration (= one directory bucket)
 #ifndef VOXB_TRI_MINBLOCKS
 #define VOXB_TRI_MINBLOCKS 6       // per-triangle kernel: 6 blocks of 128 per SM (<= 80 registers)
 #endif
@@ -658,7 +658,7 @@ __device__ __forceinline__ void tri_tile(const GridParams& g, const float* __res
 		micro = dx <= 3 && dy <= 3 && dz <= 3;
 		const unsigned long long rows = (unsigned long long)(dy + 1) * (unsigned long long)(dz + 1);
 		big = !micro;
-		items = (unsigned int)((rows + kRowsPerItem - 1) / kRowsPerItem);
+		items = (unsigned int)rows;          // work units of the cooperative kernel = (y,z) rows (G <= 65536: fits 32 bits)
 	}
 	const unsigned int slot = enqueue_warp(live && big, items, (unsigned int)i, q);
 	if (slot < q.setup_cap) store_setup(q.setups + (size_t)slot * kSetupVec, s);
@@ -787,69 +787,120 @@ __device__ __forceinline__ void surf_solve_row(const SurfSetup& s, const GridPar
 	}
 }
 
+// Writes the accepted interval [xa, xb] of row (y,z) into the table as word masks.
+template <bool MORTON>
+__device__ __forceinline__ void write_row_interval(const GridParams& g, unsigned int* __restrict__ table, int y, int z, int xa, int xb) {
+	if (MORTON) {
+		// the row in morton order: y and z are spread once, x advances in dilated form (x + 1 on bits 0,3,6,...)
+		const unsigned long long kX = 0x1249249249249249ull;
+		const unsigned long long yz = (spread3((unsigned)y) << 1) | (spread3((unsigned)z) << 2);
+		unsigned long long mx = spread3((unsigned)xa);
+		WordRun<false> run;
+		for (int x = xa; x <= xb; x++) {
+			run.add(table, g, mx | yz);
+			mx = ((mx | ~kX) + 1ull) & kX;
+		}
+		run.flush(table);
+	} else if ((g.G & 31) != 0) {
+		WordRun<false> run;
+		for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<false>(g, x, y, z));
+		run.flush(table);
+	} else {
+		// rows are whole words: first/last word get partial masks (x at bit 31 - x%32), the middle ones 0xffffffff
+		unsigned int* rowp = table + (((unsigned long long)g.G * ((unsigned long long)y + (unsigned long long)g.G * (unsigned long long)z)) >> 5) - g.word_base;
+		const int wa = xa >> 5, wb = xb >> 5;
+		const unsigned int first = 0xffffffffu >> (xa & 31), last = 0xffffffffu << (31 - (xb & 31));
+		if (wa == wb) {
+			atomicOr(rowp + wa, first & last);
+		} else {
+			atomicOr(rowp + wa, first);
+			for (int w = wa + 1; w < wb; w++) atomicOr(rowp + w, 0xffffffffu);
+			atomicOr(rowp + wb, last);
+		}
+	}
+}
+
+// The queued triangle of slot `slot`: its stored setup, or (beyond the setup buffer) the setup recomputed from the triangle.
+template <bool SOA4>
+__device__ __forceinline__ void coop_setup(const GridParams& g, const float* __restrict__ tris, const QueueView& q, unsigned int slot, unsigned int tri, SurfSetup& s) {
+	if (slot < q.setup_cap) {
+		load_setup(q.setups + (size_t)slot * kSetupVec, s);       // computed once by the per-triangle kernel
+	} else {
+		Tri t;
+		if (SOA4) load_tri_soa4(tris, g.n_tris, tri, t); else load_tri_aos(tris, tri, t);
+		shift_tri(t, g);
+		surf_setup(t, g, s);
+		clip_to_region(g, s);
+	}
+}
+
+// Persistent grid over the queued (y,z) rows: every queued triangle owns a run of consecutive row numbers (reserved
+// together with its queue slot, so the queue is sorted by first row and a directory maps every 64th row to its slot).
+// A warp takes 64 consecutive rows per iteration, whatever triangles they belong to:
+//   phase 1  every lane finds the triangle of two rows and runs the x-independent YZ tests on them (4 of the setup's 10
+//            vectors); the (slot, row) pairs that pass are compacted through shared memory;
+//   phase 2  one surviving row per lane: full setup, exact row solver, word-mask writes.
+// No lane sits out the long solve because its row failed the short test, for big triangles (all 64 rows of one
+// triangle: the setup loads are broadcasts) and small ones (several triangles per warp) alike.
 template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g, const float* __restrict__ tris,
                                                               unsigned int* __restrict__ table,
                                                               const QueueView q) {
 	const unsigned long long packed = *q.cursor;
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
-	const unsigned int n_items = (unsigned int)packed;
-	const int sub = threadIdx.x & (kRowsPerItem - 1);                       // my row within the item
-	const unsigned int group = (blockIdx.x * kBlock + threadIdx.x) / kRowsPerItem;
-	const unsigned int n_groups = (gridDim.x * kBlock) / kRowsPerItem;
-	const bool aligned = (g.G & 31) == 0;
-
-	for (unsigned int item = group; item < n_items; item += n_groups) {
-		const unsigned int lo_e = find_slot(q, item, n_entries, n_items);
-		const uint2 e = __ldg(&q.entries[lo_e]);
-		SurfSetup s;
-		if (lo_e < q.setup_cap) {
-			load_setup(q.setups + (size_t)lo_e * kSetupVec, s);       // computed once by the per-triangle kernel
-		} else {
-			Tri t;
-			if (SOA4) load_tri_soa4(tris, g.n_tris, e.x, t); else load_tri_aos(tris, e.x, t);
-			shift_tri(t, g);
-			surf_setup(t, g, s);
-			clip_to_region(g, s);
-		}
-		const int ny = s.y1 - s.y0 + 1;
-		const long long rows = (long long)ny * (long long)(s.z1 - s.z0 + 1);
-		const long long r = (long long)(item - e.y) * kRowsPerItem + sub;
-		if (r >= rows) continue;
-		const int z = s.z0 + (int)(r / ny), y = s.y0 + (int)(r % ny);
-		SurfRow row;
-		if (!surf_row(s, g, y, z, row)) continue;
-		int xa, xb;
-		surf_solve_row(s, g, row, xa, xb);
-		if (xa > xb) continue;
-		if (MORTON) {
-			// the row in morton order: y and z are spread once, x advances in dilated form (x + 1 on bits 0,3,6,...)
-			const unsigned long long kX = 0x1249249249249249ull;
-			const unsigned long long yz = (spread3((unsigned)y) << 1) | (spread3((unsigned)z) << 2);
-			unsigned long long mx = spread3((unsigned)xa);
-			WordRun<false> run;
-			for (int x = xa; x <= xb; x++) {
-				run.add(table, g, mx | yz);
-				mx = ((mx | ~kX) + 1ull) & kX;
+	const unsigned int n_rows = (unsigned int)packed;
+	__shared__ uint2 survivors[kBlock / 32][kRowsPerWarp];          // {slot, row within the triangle}
+	const int lane = threadIdx.x & 31;
+	uint2* mine = survivors[threadIdx.x >> 5];
+	const unsigned int warp = (blockIdx.x * kBlock + threadIdx.x) >> 5;
+	const unsigned int n_warps = (gridDim.x * kBlock) >> 5;
+	const unsigned int n_buckets = (n_rows + kRowsPerWarp - 1) / kRowsPerWarp;
+	for (unsigned int b = warp; b < n_buckets; b += n_warps) {
+		unsigned int pass[2];
+#pragma unroll
+		for (int h = 0; h < 2; h++) {
+			const unsigned int r = b * kRowsPerWarp + 32 * h + lane;
+			bool ok = r < n_rows;
+			unsigned int slot = 0u, local = 0u;
+			if (ok) {
+				slot = find_slot(q, r, n_entries, n_rows);
+				const uint2 e = __ldg(&q.entries[slot]);
+				local = r - e.y;
+				if (slot < q.setup_cap) {
+					// the YZ part of the stored setup: yz_a, yz_b, yz_d and the bbox (vectors 3, 4, 5, 8)
+					const uint4* sp = q.setups + (size_t)slot * kSetupVec;
+					const uint4 v3 = __ldg(sp + 3), v4 = __ldg(sp + 4), v5 = __ldg(sp + 5), v8 = __ldg(sp + 8);
+					const int y0 = (int)(v8.y & 0xffffu), ny = (int)(v8.y >> 16) - y0 + 1, z0 = (int)(v8.z & 0xffffu);
+					const int y = y0 + (int)(local % (unsigned int)ny), z = z0 + (int)(local / (unsigned int)ny);
+					const float py = fmul((float)y, g.uy), pz = fmul((float)z, g.uz);
+					ok = !(fadd(dot2(__uint_as_float(v3.z), __uint_as_float(v4.y), py, pz), __uint_as_float(v5.x)) < 0.0f) &&
+					     !(fadd(dot2(__uint_as_float(v3.w), __uint_as_float(v4.z), py, pz), __uint_as_float(v5.y)) < 0.0f) &&
+					     !(fadd(dot2(__uint_as_float(v4.x), __uint_as_float(v4.w), py, pz), __uint_as_float(v5.z)) < 0.0f);
+				} else {
+					SurfSetup s;
+					coop_setup<SOA4>(g, tris, q, slot, e.x, s);
+					const int ny = s.y1 - s.y0 + 1;
+					ok = surf_row_passes_yz(s, g, s.y0 + (int)(local % (unsigned int)ny), s.z0 + (int)(local / (unsigned int)ny));
+				}
 			}
-			run.flush(table);
-		} else if (!aligned) {
-			WordRun<false> run;
-			for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<false>(g, x, y, z));
-			run.flush(table);
-		} else {
-			// rows are whole words: first/last word get partial masks (x at bit 31 - x%32), the middle ones 0xffffffff
-			unsigned int* rowp = table + (((unsigned long long)g.G * ((unsigned long long)y + (unsigned long long)g.G * (unsigned long long)z)) >> 5) - g.word_base;
-			const int wa = xa >> 5, wb = xb >> 5;
-			const unsigned int first = 0xffffffffu >> (xa & 31), last = 0xffffffffu << (31 - (xb & 31));
-			if (wa == wb) {
-				atomicOr(rowp + wa, first & last);
-			} else {
-				atomicOr(rowp + wa, first);
-				for (int w = wa + 1; w < wb; w++) atomicOr(rowp + w, 0xffffffffu);
-				atomicOr(rowp + wb, last);
-			}
+			pass[h] = __ballot_sync(0xffffffffu, ok);
+			if (ok) mine[(h ? __popc(pass[0]) : 0) + __popc(pass[h] & ((1u << lane) - 1u))] = make_uint2(slot, local);
 		}
+		const int n = __popc(pass[0]) + __popc(pass[1]);
+		__syncwarp();
+		for (int k = lane; k < n; k += 32) {
+			const uint2 sr = mine[k];
+			SurfSetup s;
+			coop_setup<SOA4>(g, tris, q, sr.x, sr.x < q.setup_cap ? 0u : __ldg(&q.entries[sr.x].x), s);
+			const int ny = s.y1 - s.y0 + 1;
+			const int z = s.z0 + (int)(sr.y / (unsigned int)ny), y = s.y0 + (int)(sr.y % (unsigned int)ny);
+			SurfRow row;
+			surf_row_values(s, g, y, z, row);
+			int xa, xb;
+			surf_solve_row(s, g, row, xa, xb);
+			if (xa <= xb) write_row_interval<MORTON>(g, table, y, z, xa, xb);
+		}
+		__syncwarp();
 	}
 }
 

@@ -269,16 +269,26 @@ struct SurfRow {
 	float zx_apz[3];             // n_zx_e.x * p.z
 };
 
-// Returns false when the three YZ edge tests (:150-153, x-independent) reject the whole row.
-__device__ __forceinline__ bool surf_row(const SurfSetup& s, const GridParams& g, int y, int z, SurfRow& r) {
+// The three YZ edge tests (:150-153): x-independent, so they accept or reject a whole (y,z) row.
+__device__ __forceinline__ bool surf_row_passes_yz(const SurfSetup& s, const GridParams& g, int y, int z) {
 	const float py = fmul((float)y, g.uy), pz = fmul((float)z, g.uz);       // :138
 #pragma unroll
 	for (int k = 0; k < 3; k++)
 		if (fadd(dot2(s.yz_a[k], s.yz_b[k], py, pz), s.yz_d[k]) < 0.0f) return false;
+	return true;
+}
+// The hoisted per-row products of a row that passed.
+__device__ __forceinline__ void surf_row_values(const SurfSetup& s, const GridParams& g, int y, int z, SurfRow& r) {
+	const float py = fmul((float)y, g.uy), pz = fmul((float)z, g.uz);
 	r.ny_py = fmul(s.ny, py);
 	r.nz_pz = fmul(s.nz, pz);
 #pragma unroll
 	for (int k = 0; k < 3; k++) { r.xy_bpy[k] = fmul(s.xy_b[k], py); r.zx_apz[k] = fmul(s.zx_a[k], pz); }
+}
+// Returns false when the YZ tests reject the whole row.
+__device__ __forceinline__ bool surf_row(const SurfSetup& s, const GridParams& g, int y, int z, SurfRow& r) {
+	if (!surf_row_passes_yz(s, g, y, z)) return false;
+	surf_row_values(s, g, y, z, r);
 	return true;
 }
 
@@ -455,7 +465,8 @@ __device__ __forceinline__ void load_tri_block_aos(const float* __restrict__ tri
 // ---------------------------------------------------------------------------------------------
 // Work queue of the cooperative (large-triangle) kernels
 // ---------------------------------------------------------------------------------------------
-// Reserves, for every pushing lane of the warp, one queue slot and `items` consecutive work items with a
+// Work units: (y,z) rows for the surface path, blocks of kSamplesPerItem centre samples for the solid path.
+// Reserves, for every pushing lane of the warp, one queue slot and `items` consecutive work units with a
 // single packed atomicAdd ((slots << 32) | items).  Because both halves advance together, queue[] ends
 // up sorted by first-item, which is what lets the cooperative kernel binary-search item -> triangle.
 // The cooperative-path work queue as the kernels see it.
