@@ -496,12 +496,23 @@ __device__ __forceinline__ unsigned int enqueue_warp(bool push, unsigned int ite
 	unsigned long long base = 0ull;
 	if (lane == 0) base = atomicAdd(q.cursor, ((unsigned long long)__popc(pushers) << 32) | (unsigned long long)total);
 	base = __shfl_sync(0xffffffffu, base, 0);
-	if (!push) return 0xffffffffu;
-	const unsigned int slot = (unsigned int)(base >> 32) + __popc(pushers & ((1u << lane) - 1u));
+	const unsigned int slot = push ? (unsigned int)(base >> 32) + __popc(pushers & ((1u << lane) - 1u)) : 0xffffffffu;
 	const unsigned int first = (unsigned int)base + (incl - mine);
-	q.entries[slot] = make_uint2(tri, first);
-	// every multiple of 64 inside [first, first + items) gets this slot in the directory
-	for (unsigned int b = (first + (1u << kDirShift) - 1u) >> kDirShift; b < q.dir_cap && (b << kDirShift) < first + items; b++) q.dir[b] = slot;
+	if (push) q.entries[slot] = make_uint2(tri, first);
+	// every multiple of 64 inside [first, first + items) gets this slot in the directory: short ranges by their own lane,
+	// long ones (a triangle of a million rows has 16 k entries) by the whole warp, one pusher after the other
+	const unsigned int b0 = (first + (1u << kDirShift) - 1u) >> kDirShift;
+	const unsigned long long end = (unsigned long long)first + mine;
+	const unsigned int b1 = (unsigned int)min((unsigned long long)q.dir_cap, (end + (1ull << kDirShift) - 1ull) >> kDirShift);      // one past the last bucket
+	const bool wide = push && b1 > b0 + 8u;
+	if (push && !wide) for (unsigned int b = b0; b < b1; b++) q.dir[b] = slot;
+	unsigned int todo = __ballot_sync(0xffffffffu, wide);
+	while (todo) {
+		const int src = __ffs(todo) - 1;
+		todo &= todo - 1u;
+		const unsigned int f0 = __shfl_sync(0xffffffffu, b0, src), f1 = __shfl_sync(0xffffffffu, b1, src), sl = __shfl_sync(0xffffffffu, slot, src);
+		for (unsigned int b = f0 + lane; b < f1; b += 32u) q.dir[b] = sl;
+	}
 	return slot;
 }
 
