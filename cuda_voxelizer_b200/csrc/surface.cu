@@ -42,9 +42,6 @@ constexpr int kRowsPerWarp = 64;   // consecutive queued (y,z) rows one warp of 
 #ifndef VOXB_DEBUG_WINDOW_WORDS
 #define VOXB_DEBUG_WINDOW_WORDS 0x400000u
 #endif
-#ifndef VOXB_UNROLLED_SCATTER
-#define VOXB_UNROLLED_SCATTER 1
-#endif
 #if VOXB_TRI_MINBLOCKS > 0
 #define VOXB_TRI_BOUNDS __launch_bounds__(kTriBlock, VOXB_TRI_MINBLOCKS)
 #else
@@ -113,7 +110,6 @@ __device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {   
 	return __funnelshift_l(__float_as_uint(v), mask, 1);
 }
 
-#if VOXB_PACKED
 // The nine sums a[i] + b[j] of a 3x3 cell block in five additions (four of them FADD2), and one more level `+ d`
 // in five again: p[j] = cells (0,j),(1,j); q = cells (2,0),(2,1) (computed as b + a: IEEE addition commutes bit
 // for bit); r = cell (2,2).
@@ -309,183 +305,6 @@ __device__ __forceinline__ unsigned long long surf_micro4(const SurfSetup& s, co
 	}
 	return hit;
 }
-#else   // scalar evaluation (one FADD per addition), kept for A/B measurement
-__device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const GridParams& g) {
-	float px[3], py[3], pz[3];
-#pragma unroll
-	for (int i = 0; i < 3; i++) {
-		px[i] = fmul((float)(s.x0 + i), g.ux);
-		py[i] = fmul((float)(s.y0 + i), g.uy);
-		pz[i] = fmul((float)(s.z0 + i), g.uz);
-	}
-	// plane: ((n.x*p.x + n.y*p.y) + n.z*p.z), then (s + d1) * (s + d2) > 0 rejects
-	float nxp[3], nyp[3], nzp[3];
-#pragma unroll
-	for (int i = 0; i < 3; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
-	unsigned int rej = 0u;
-#pragma unroll
-	for (int k = 2; k >= 0; k--)
-#pragma unroll
-		for (int j = 2; j >= 0; j--)
-#pragma unroll
-			for (int i = 0; i < 3; i++) {               // x ascending: x0 ends up at the HIGH bit of its row (MSB-first, like the table)
-				const float sdp = fadd(fadd(nxp[i], nyp[j]), nzp[k]);
-				const float prod = fmul(fadd(sdp, s.d1), fadd(sdp, s.d2));
-				rej = sign_in(rej, fsub(0.0f, prod));
-			}
-	// XY cells (i,j): bit i + 3j, replicated over k
-	unsigned int rxy = 0u, ryz = 0u, rzx = 0u;
-	{
-		float a[3][3], b[3][3];
-#pragma unroll
-		for (int e = 0; e < 3; e++)
-#pragma unroll
-			for (int i = 0; i < 3; i++) { a[e][i] = fmul(s.xy_a[e], px[i]); b[e][i] = fmul(s.xy_b[e], py[i]); }
-#pragma unroll
-		for (int j = 2; j >= 0; j--)
-#pragma unroll
-			for (int i = 0; i < 3; i++) {
-				const float v0 = fadd(fadd(a[0][i], b[0][j]), s.xy_d[0]);
-				const float v1 = fadd(fadd(a[1][i], b[1][j]), s.xy_d[1]);
-				const float v2 = fadd(fadd(a[2][i], b[2][j]), s.xy_d[2]);
-				rxy = sign_in(rxy, fminf(fminf(v0, v1), v2));
-			}
-	}
-	// YZ cells (j,k): value = (n.x*p.y + n.y*p.z) + d; bit j + 3k, replicated over i
-	{
-		float a[3][3], b[3][3];
-#pragma unroll
-		for (int e = 0; e < 3; e++)
-#pragma unroll
-			for (int i = 0; i < 3; i++) { a[e][i] = fmul(s.yz_a[e], py[i]); b[e][i] = fmul(s.yz_b[e], pz[i]); }
-#pragma unroll
-		for (int k = 2; k >= 0; k--)
-#pragma unroll
-			for (int j = 2; j >= 0; j--) {
-				const float v0 = fadd(fadd(a[0][j], b[0][k]), s.yz_d[0]);
-				const float v1 = fadd(fadd(a[1][j], b[1][k]), s.yz_d[1]);
-				const float v2 = fadd(fadd(a[2][j], b[2][k]), s.yz_d[2]);
-				ryz = sign_in(ryz, fminf(fminf(v0, v1), v2));
-			}
-	}
-	// ZX cells (k,i): value = (n.x*p.z + n.y*p.x) + d; bit i + 3k, replicated over j
-	{
-		float a[3][3], b[3][3];
-#pragma unroll
-		for (int e = 0; e < 3; e++)
-#pragma unroll
-			for (int i = 0; i < 3; i++) { a[e][i] = fmul(s.zx_a[e], pz[i]); b[e][i] = fmul(s.zx_b[e], px[i]); }
-#pragma unroll
-		for (int k = 2; k >= 0; k--)
-#pragma unroll
-			for (int i = 0; i < 3; i++) {
-				const float v0 = fadd(fadd(a[0][k], b[0][i]), s.zx_d[0]);
-				const float v1 = fadd(fadd(a[1][k], b[1][i]), s.zx_d[1]);
-				const float v2 = fadd(fadd(a[2][k], b[2][i]), s.zx_d[2]);
-				rzx = sign_in(rzx, fminf(fminf(v0, v1), v2));
-			}
-	}
-	// expand the 9-bit cell masks to the 27-bit voxel layout b = (2-i) + 3j + 9k
-	const unsigned int xy27 = rxy * 0x40201u;                                           // copies at +0, +9, +18
-	const unsigned int yz_s = (ryz & 0x1u) | ((ryz & 0x2u) << 2) | ((ryz & 0x4u) << 4) | ((ryz & 0x8u) << 6) | ((ryz & 0x10u) << 8) |
-	                          ((ryz & 0x20u) << 10) | ((ryz & 0x40u) << 12) | ((ryz & 0x80u) << 14) | ((ryz & 0x100u) << 16);   // bit (j+3k) -> 3j+9k
-	const unsigned int yz27 = yz_s * 7u;                                                // copies at +0, +1, +2
-	const unsigned int zx_s = (rzx & 0x7u) | ((rzx & 0x38u) << 6) | ((rzx & 0x1c0u) << 12);                                     // bit (i+3k) -> i+9k
-	const unsigned int zx27 = zx_s * 0x49u;                                             // copies at +0, +3, +6
-	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..2
-	const unsigned int valid = (((7u << (2 - ex)) & 7u) * 0x1249249u) & (((8u << (3 * ey)) - 1u) * 0x40201u) & ((512u << (9 * ez)) - 1u);
-	return valid & ~(rej | xy27 | yz27 | zx27);
-}
-
-// The same branch-free evaluation for a bbox of at most 4x4x4 voxels (triangles up to ~3 voxels across, whatever their
-// alignment).  64 candidates: bit (3-i) + 4j + 16k of the result = voxel (x0+i, y0+j, z0+k), built as four 16-bit
-// z-slices.  Used for the whole warp as soon as one of its triangles does not fit 3x3x3.
-__device__ __forceinline__ unsigned long long surf_micro4(const SurfSetup& s, const GridParams& g) {
-	float px[4], py[4], pz[4];
-#pragma unroll
-	for (int i = 0; i < 4; i++) {
-		px[i] = fmul((float)(s.x0 + i), g.ux);
-		py[i] = fmul((float)(s.y0 + i), g.uy);
-		pz[i] = fmul((float)(s.z0 + i), g.uz);
-	}
-	float nxp[4], nyp[4], nzp[4];
-#pragma unroll
-	for (int i = 0; i < 4; i++) { nxp[i] = fmul(s.nx, px[i]); nyp[i] = fmul(s.ny, py[i]); nzp[i] = fmul(s.nz, pz[i]); }
-	unsigned int rej[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-	for (int k = 0; k < 4; k++)
-#pragma unroll
-		for (int j = 3; j >= 0; j--)
-#pragma unroll
-			for (int i = 0; i < 4; i++) {
-				const float sdp = fadd(fadd(nxp[i], nyp[j]), nzp[k]);
-				const float prod = fmul(fadd(sdp, s.d1), fadd(sdp, s.d2));
-				rej[k] = sign_in(rej[k], fsub(0.0f, prod));
-			}
-	unsigned int rxy = 0u, ryz = 0u, rzx = 0u;          // 16 cells each: (i,j) -> (3-i)+4j, (j,k) -> j+4k, (k,i) -> (3-i)+4k
-	{
-		float a[3][4], b[3][4];
-#pragma unroll
-		for (int e = 0; e < 3; e++)
-#pragma unroll
-			for (int i = 0; i < 4; i++) { a[e][i] = fmul(s.xy_a[e], px[i]); b[e][i] = fmul(s.xy_b[e], py[i]); }
-#pragma unroll
-		for (int j = 3; j >= 0; j--)
-#pragma unroll
-			for (int i = 0; i < 4; i++) {
-				const float v0 = fadd(fadd(a[0][i], b[0][j]), s.xy_d[0]);
-				const float v1 = fadd(fadd(a[1][i], b[1][j]), s.xy_d[1]);
-				const float v2 = fadd(fadd(a[2][i], b[2][j]), s.xy_d[2]);
-				rxy = sign_in(rxy, fminf(fminf(v0, v1), v2));
-			}
-	}
-	{
-		float a[3][4], b[3][4];
-#pragma unroll
-		for (int e = 0; e < 3; e++)
-#pragma unroll
-			for (int i = 0; i < 4; i++) { a[e][i] = fmul(s.yz_a[e], py[i]); b[e][i] = fmul(s.yz_b[e], pz[i]); }
-#pragma unroll
-		for (int k = 3; k >= 0; k--)
-#pragma unroll
-			for (int j = 3; j >= 0; j--) {
-				const float v0 = fadd(fadd(a[0][j], b[0][k]), s.yz_d[0]);
-				const float v1 = fadd(fadd(a[1][j], b[1][k]), s.yz_d[1]);
-				const float v2 = fadd(fadd(a[2][j], b[2][k]), s.yz_d[2]);
-				ryz = sign_in(ryz, fminf(fminf(v0, v1), v2));
-			}
-	}
-	{
-		float a[3][4], b[3][4];
-#pragma unroll
-		for (int e = 0; e < 3; e++)
-#pragma unroll
-			for (int i = 0; i < 4; i++) { a[e][i] = fmul(s.zx_a[e], pz[i]); b[e][i] = fmul(s.zx_b[e], px[i]); }
-#pragma unroll
-		for (int k = 3; k >= 0; k--)
-#pragma unroll
-			for (int i = 0; i < 4; i++) {
-				const float v0 = fadd(fadd(a[0][k], b[0][i]), s.zx_d[0]);
-				const float v1 = fadd(fadd(a[1][k], b[1][i]), s.zx_d[1]);
-				const float v2 = fadd(fadd(a[2][k], b[2][i]), s.zx_d[2]);
-				rzx = sign_in(rzx, fminf(fminf(v0, v1), v2));
-			}
-	}
-	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..3
-	const unsigned int valid_xy = (((0xfu << (3 - ex)) & 0xfu) * 0x1111u) & ((16u << (4 * ey)) - 1u);
-	unsigned long long hit = 0ull;
-#pragma unroll
-	for (int k = 3; k >= 0; k--) {
-		const unsigned int m = (ryz >> (4 * k)) & 0xfu;                                  // row bits j of slice k -> 4 bits each
-		const unsigned int yz16 = ((m & 1u) | ((m & 2u) << 3) | ((m & 4u) << 6) | ((m & 8u) << 9)) * 0xfu;
-		const unsigned int zx16 = ((rzx >> (4 * k)) & 0xfu) * 0x1111u;                   // x bits of slice k, copied to every row
-		const unsigned int h = (k <= ez) ? (valid_xy & ~(rej[k] | rxy | yz16 | zx16)) : 0u;
-		hit = (hit << 16) | (unsigned long long)(h & 0xffffu);
-	}
-	return hit;
-}
-
-#endif
 
 // Writes a 64-bit hit mask of surf_micro4 into the table, one (y,z) row — four x-adjacent bits — at a time.
 template <bool MORTON>
@@ -542,7 +361,6 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 		const unsigned int Gw = (unsigned int)g.G >> 5;
 		const unsigned int w0 = Gw * ((unsigned int)y0 + (unsigned int)g.G * (unsigned int)z0) + ((unsigned int)x0 >> 5) - (unsigned int)g.word_base;
 		const unsigned int sh = (unsigned int)x0 & 31u;
-#if VOXB_UNROLLED_SCATTER
 		// straight-line: the nine rows one after the other, each write predicated on its bits (no loop, no divergence)
 		unsigned int* p = table + w0;
 		const unsigned int layer = Gw * (unsigned int)g.G;
@@ -566,19 +384,6 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 				if (lo) red_or(q + 1, lo);
 #endif
 			}
-#else
-		while (hit) {
-			const int r = (__ffs(hit) - 1) / 3;                    // row = j + 3k
-			const unsigned int bits = (hit >> (3 * r)) & 7u;        // x0 at bit 2 ... x0+2 at bit 0
-			hit &= ~(7u << (3 * r));
-			const int k = r / 3, j = r - 3 * k;
-			const unsigned int w = w0 + Gw * ((unsigned int)j + (unsigned int)g.G * (unsigned int)k);
-			const unsigned int v = bits << 29;                      // x0 -> bit 31, x0+1 -> 30, x0+2 -> 29
-			const unsigned int hi = v >> sh, lo = __funnelshift_r(0u, v, sh);
-			if (hi) atomicOr(table + w, hi);
-			if (lo) atomicOr(table + w + 1, lo);
-		}
-#endif
 		return;
 	}
 	const unsigned long long G = (unsigned long long)g.G;
@@ -672,13 +477,11 @@ __device__ __forceinline__ void tri_tile(const GridParams& g, const float* __res
 		if (hit4) scatter_hits4<MORTON>(hit4, s.x0, s.y0, s.z0, g, table);
 		return;
 	}
-#if VOXB_UNROLLED_SCATTER
 	if (!MORTON && (g.G & 31) == 0 && g.G <= 4096) {
 		if (!mine) { s.x0 = 0; s.y0 = 0; s.z0 = 0; }
 		scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);     // converged: every write is predicated on its own bits
 		return;
 	}
-#endif
 	if (hit) scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);
 }
 

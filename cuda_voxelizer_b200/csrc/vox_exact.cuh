@@ -38,9 +38,6 @@ __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b)
 // mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under -fmad=false, whereas it never fuses a scalar FMUL into a
 // packed add — products therefore stay scalar (tests/test_abi.py checks the SASS holds no FFMA2 / FMUL2).
 // A scalar broadcast operand (bc) costs nothing: FADD2 takes `R.F32` as its second source.
-#ifndef VOXB_PACKED
-#define VOXB_PACKED 1
-#endif
 __device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
 __device__ __forceinline__ float2 fsub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }   // a - b == a + (-b), bit for bit
 __device__ __forceinline__ float2 bc(float s) { return make_float2(s, s); }
@@ -63,17 +60,11 @@ struct Tri {
 
 // cpu_voxelizer.cpp:40-45 / voxelize.cu:71-73 — the vertex shift, one rounded subtraction per coordinate
 __device__ __forceinline__ void shift_tri(Tri& t, const GridParams& g) {
-#if VOXB_PACKED
 	const float2 bxy = make_float2(g.bx, g.by);
 	const float2 a = fsub2(make_float2(t.v0x, t.v0y), bxy), b = fsub2(make_float2(t.v1x, t.v1y), bxy), c = fsub2(make_float2(t.v2x, t.v2y), bxy);
 	const float2 z01 = fsub2(make_float2(t.v0z, t.v1z), bc(g.bz));
 	t.v0x = a.x; t.v0y = a.y; t.v1x = b.x; t.v1y = b.y; t.v2x = c.x; t.v2y = c.y;
 	t.v0z = z01.x; t.v1z = z01.y; t.v2z = fsub(t.v2z, g.bz);
-#else
-	t.v0x = fsub(t.v0x, g.bx); t.v0y = fsub(t.v0y, g.by); t.v0z = fsub(t.v0z, g.bz);
-	t.v1x = fsub(t.v1x, g.bx); t.v1y = fsub(t.v1y, g.by); t.v1z = fsub(t.v1z, g.bz);
-	t.v2x = fsub(t.v2x, g.bx); t.v2y = fsub(t.v2y, g.by); t.v2z = fsub(t.v2z, g.bz);
-#endif
 }
 
 // normalize(cross(e0, e1)) — cpu_voxelizer.cpp:72 with helper_math.h:1436 (cross), :1325 + :78 (normalize)
@@ -137,7 +128,6 @@ __device__ __forceinline__ void surf_bbox(const Tri& t, const GridParams& g, Sur
 }
 
 // Everything but the bbox: normal, plane offsets, the 9 edge functions.
-#if VOXB_PACKED
 // The nine edge functions at once: products scalar, the 27 additions of the nine d_e as 15 (12 of them FADD2).
 // Edge q = 3*plane + e.  d = ((-dot(n_e, v)) + max(0, ua*n_e.x)) + max(0, ub*n_e.y), left to right as in edge_setup;
 // -1*x is the exact negation of x.
@@ -192,36 +182,6 @@ __device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams&
 		s.zx_a[e] = na[6 + e]; s.zx_b[e] = nb[6 + e]; s.zx_d[e] = d[6 + e];
 	}
 }
-#else
-__device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams& g, SurfSetup& s) {
-	// :68-70 edges
-	float e0x = fsub(t.v1x, t.v0x), e0y = fsub(t.v1y, t.v0y), e0z = fsub(t.v1z, t.v0z);
-	float e1x = fsub(t.v2x, t.v1x), e1y = fsub(t.v2y, t.v1y), e1z = fsub(t.v2z, t.v1z);
-	float e2x = fsub(t.v0x, t.v2x), e2y = fsub(t.v0y, t.v2y), e2z = fsub(t.v0z, t.v2z);
-	tri_normal(e0x, e0y, e0z, e1x, e1y, e1z, s.nx, s.ny, s.nz);
-	// :83-87 plane offsets
-	float cx = (s.nx > 0.0f) ? g.ux : 0.0f;
-	float cy = (s.ny > 0.0f) ? g.uy : 0.0f;
-	float cz = (s.nz > 0.0f) ? g.uz : 0.0f;
-	s.d1 = dot3(s.nx, s.ny, s.nz, fsub(cx, t.v0x), fsub(cy, t.v0y), fsub(cz, t.v0z));
-	s.d2 = dot3(s.nx, s.ny, s.nz, fsub(fsub(g.ux, cx), t.v0x), fsub(fsub(g.uy, cy), t.v0y), fsub(fsub(g.uz, cz), t.v0z));
-	// :91-101 XY  (n_e = (-e.y, e.x), flipped if n.z < 0; offsets pair unit.x/unit.y)
-	const bool fz = s.nz < 0.0f, fx = s.nx < 0.0f, fy = s.ny < 0.0f;
-	edge_setup(e0y, e0x, fz, t.v0x, t.v0y, g.ux, g.uy, s.xy_a[0], s.xy_b[0], s.xy_d[0]);
-	edge_setup(e1y, e1x, fz, t.v1x, t.v1y, g.ux, g.uy, s.xy_a[1], s.xy_b[1], s.xy_d[1]);
-	edge_setup(e2y, e2x, fz, t.v2x, t.v2y, g.ux, g.uy, s.xy_a[2], s.xy_b[2], s.xy_d[2]);
-	// :103-113 YZ  (n_e = (-e.z, e.y), flipped if n.x < 0; offsets pair unit.y/unit.z)
-	edge_setup(e0z, e0y, fx, t.v0y, t.v0z, g.uy, g.uz, s.yz_a[0], s.yz_b[0], s.yz_d[0]);
-	edge_setup(e1z, e1y, fx, t.v1y, t.v1z, g.uy, g.uz, s.yz_a[1], s.yz_b[1], s.yz_d[1]);
-	edge_setup(e2z, e2y, fx, t.v2y, t.v2z, g.uy, g.uz, s.yz_a[2], s.yz_b[2], s.yz_d[2]);
-	// :115-125 ZX  (n_e = (-e.x, e.z), flipped if n.y < 0).  The reference pairs unit.X with the
-	// first component (the coefficient of p.z) and unit.Z with the second (§A-13): kept verbatim.
-	edge_setup(e0x, e0z, fy, t.v0z, t.v0x, g.ux, g.uz, s.zx_a[0], s.zx_b[0], s.zx_d[0]);
-	edge_setup(e1x, e1z, fy, t.v1z, t.v1x, g.ux, g.uz, s.zx_a[1], s.zx_b[1], s.zx_d[1]);
-	edge_setup(e2x, e2z, fy, t.v2z, t.v2x, g.ux, g.uz, s.zx_a[2], s.zx_b[2], s.zx_d[2]);
-}
-
-#endif
 
 __device__ __forceinline__ void surf_setup(const Tri& t, const GridParams& g, SurfSetup& s) {
 	surf_bbox(t, g, s);
