@@ -2,6 +2,7 @@
 // over the C ABI.  Behavioural contract copied from the reference launchers (voxelize.cu:192-238,
 // voxelize_solid.cu:147-193): synchronous, times the device work with CUDA events, prints the
 // "[Perf]" line, and turns any failure into print + exit(EXIT_FAILURE).
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstddef>
@@ -35,6 +36,12 @@ void run(bool solid, const voxinfo& v, float* triangle_data, unsigned int* vtabl
 	cudaEventRecord(stop_vox, 0);
 	cudaError_t e = cudaDeviceSynchronize();
 	if (e != cudaSuccess) { fprintf(stderr, "CUDA error at voxelize: code=%d(%s) \n", (int)e, cudaGetErrorName(e)); exit(EXIT_FAILURE); }
+	uint64_t counters[4] = {0, 0, 0, 0};
+	if (voxb200_last_counters(counters) != VOXB200_OK) die("voxb200_last_counters", VOXB200_ECUDA);
+	if (counters[1] == ~0ull) {
+		fprintf(stderr, "voxelize: more than 2^32 (y,z) rows queued for the large-triangle path; the table is not valid \n");
+		exit(EXIT_FAILURE);
+	}
 	float elapsed = 0.0f;
 	cudaEventElapsedTime(&elapsed, start_vox, stop_vox);
 	printf("[Perf] Voxelization GPU time: %.1f ms\n", elapsed);

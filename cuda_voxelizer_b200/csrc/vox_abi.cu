@@ -558,7 +558,10 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 	CU(cudaEventRecord(hp.ev[2], st));
 	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(hp.ev[3], st));
+	unsigned long long overflow = 0ull;
+	CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
 	if (timing_ms) {
 		CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
 		CU(cudaEventElapsedTime(&timing_ms[1], hp.ev[1], hp.ev[2]));
@@ -600,7 +603,10 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 	CU(cudaEventRecord(hp.ev[2], st));
 	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(hp.ev[3], st));
+	unsigned long long overflow = 0ull;
+	CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
 	if (timing_ms) {
 		CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
 		CU(cudaEventElapsedTime(&timing_ms[1], hp.ev[1], hp.ev[2]));
@@ -700,7 +706,7 @@ int voxb200_last_counters(uint64_t out[4]) {
 	unsigned long long c[kNumCounters];
 	CU(cudaMemcpy(c, ws->counters, sizeof(c), cudaMemcpyDeviceToHost));
 	out[0] = c[kCtrQueue] >> 32;
-	out[1] = c[kCtrQueue] & 0xffffffffull;
+	out[1] = c[kCtrQueueOverflow] ? ~0ull : (c[kCtrQueue] & 0xffffffffull);
 	out[2] = c[kCtrSolidClamp];
 	out[3] = ws->last_row_lists ? 1 : 0;
 	return VOXB200_OK;

@@ -454,7 +454,11 @@ __device__ __forceinline__ unsigned int enqueue_warp(bool push, unsigned int ite
 	}
 	const unsigned int total = __shfl_sync(0xffffffffu, incl, 31);
 	unsigned long long base = 0ull;
-	if (lane == 0) base = atomicAdd(q.cursor, ((unsigned long long)__popc(pushers) << 32) | (unsigned long long)total);
+	if (lane == 0) {
+		base = atomicAdd(q.cursor, ((unsigned long long)__popc(pushers) << 32) | (unsigned long long)total);
+		// the unit count lives in 32 bits: a call that queues more than 2^32 rows is flagged (cursor[3]) and reported by the host side
+		if ((unsigned int)base + total < (unsigned int)base) atomicAdd(q.cursor + 3, 1ull);
+	}
 	base = __shfl_sync(0xffffffffu, base, 0);
 	const unsigned int slot = push ? (unsigned int)(base >> 32) + __popc(pushers & ((1u << lane) - 1u)) : 0xffffffffu;
 	const unsigned int first = (unsigned int)base + (incl - mine);

@@ -51,6 +51,7 @@ enum Counter {
 	kCtrQueue = 0,        // packed: (queue entries << 32) | work items
 	kCtrClaim = 1,        // next work item to hand out (dynamic scheduling)
 	kCtrSolidClamp = 2,   // solid samples whose xmax fell outside [0, G-1]
+	kCtrQueueOverflow = 3,   // the work-unit half of kCtrQueue wrapped (more than 2^32 queued rows / sample blocks in one call)
 	kNumCounters = 8
 };
 

@@ -184,7 +184,8 @@ int voxb200_extract_voxels(const unsigned int* d_table, size_t table_words, uint
 uint64_t voxb200_launch_count(int reset);
 /* Counters of the last surface/solid call, valid after the stream has been synchronised:
  * [0] triangles routed to the cooperative (large-triangle) path, [1] work units of that path ((y,z) rows for the surface
- * path, blocks of 256 centre samples for the solid path),
+ * path, blocks of 256 centre samples for the solid path; UINT64_MAX when more than 2^32 units were queued in one call — the
+ * table contents are undefined then; voxb200_voxelize_host* and the C++ drop-in symbols report it as an error),
  * [2] solid: samples clamped because xmax fell outside [0, G-1] (reference UB territory),
  * [3] 1 when the last voxb200_solid call used per-row mark lists + a single fill pass (no zero-fill, no scan) — host-side state. */
 int voxb200_last_counters(uint64_t out[4]);

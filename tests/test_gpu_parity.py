@@ -370,6 +370,23 @@ def test_cuda_graph_capture_and_replay(vb, solid):
         assert torch.equal(table, want)
 
 
+def test_queue_unit_overflow_is_reported(vb):
+    """The large-triangle queue counts its work units ((y,z) rows) in 32 bits.  A soup that queues more than 2^32 rows in
+    one call must be reported (last_counters, and an error from the synchronous host entry point), not silently mangled."""
+    g, n = 1024, 4600                                   # 4600 triangles spanning the whole grid: 4600 * 2^20 rows > 2^32
+    tri = np.array([0, 0, 0, 1, 1, 0.9, 0.1, 1, 1], np.float32)
+    soup = np.tile(tri, (n, 1))
+    grid = vb.grid_from_verts(soup.reshape(-1, 3), g, n)
+    vb.voxelize(grid, torch.from_numpy(soup).cuda())
+    torch.cuda.synchronize()
+    assert vb.last_counters()["coop_items"] == 2 ** 64 - 1
+    with pytest.raises(vb.VoxError):
+        vb.voxelize_host(grid, soup)
+    # a normal call afterwards is unaffected
+    table, _ = _run(vb, "bunny", 64, 0, 0)
+    assert vb.last_counters()["coop_items"] < 2 ** 32
+
+
 def test_release_and_reuse(vb):
     """voxb200_release frees the cached scratch; the next call rebuilds it and gives the same table."""
     name, g = "bunny", 64
