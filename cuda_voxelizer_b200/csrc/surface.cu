@@ -32,6 +32,7 @@ namespace voxb {
 
 constexpr int kBlock = 256;        // cooperative kernel
 constexpr int kTriBlock = 128;     // per-triangle kernel: 4 warps, each with its own staging slab
+constexpr int kSweepWidth = 8;     // cooperative kernel: rows narrower than this are swept voxel by voxel instead of solved
 constexpr int kRowsPerWarp = 64;   // consecutive queued (y,z) rows one warp of the cooperative kernel takes per iteration (= one directory bucket)
 #ifndef VOXB_TRI_MINBLOCKS
 #define VOXB_TRI_MINBLOCKS 6       // per-triangle kernel: 6 blocks of 128 per SM (<= 80 registers)
@@ -699,6 +700,17 @@ __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g
 			const int z = s.z0 + (int)(sr.y / (unsigned int)ny), y = s.y0 + (int)(sr.y % (unsigned int)ny);
 			SurfRow row;
 			surf_row_values(s, g, y, z, row);
+			if (!MORTON && (g.G & 31) == 0 && s.x1 - s.x0 < kSweepWidth) {
+				// a narrow row (triangles of a few voxels): testing its voxels one by one costs less than locating interval ends
+				unsigned int m = 0u;
+#pragma unroll 1
+				for (int x = s.x0; x <= s.x1; x++) m |= surf_voxel(s, g, row, x) ? 0x80000000u >> (x - s.x0) : 0u;      // x0 at bit 31, MSB first like the table
+				unsigned int* rowp = table + (((unsigned long long)g.G * ((unsigned long long)y + (unsigned long long)g.G * (unsigned long long)z)) >> 5) - g.word_base + (s.x0 >> 5);
+				const unsigned int sh = (unsigned int)s.x0 & 31u, hi = m >> sh, lo = __funnelshift_r(0u, m, sh);
+				if (hi) atomicOr(rowp, hi);
+				if (lo) atomicOr(rowp + 1, lo);
+				continue;
+			}
 			int xa, xb;
 			surf_solve_row(s, g, row, xa, xb);
 			if (xa <= xb) write_row_interval<MORTON>(g, table, y, z, xa, xb);
