@@ -153,9 +153,9 @@ def run_reference(args):
         total_ms += ms
     ms_per_step = total_ms / args.steps
     value = n_sample / ms_per_step / 1e3
-    sample = ("first %d of %d triangles of the workload per step, whole 2048^3 grid; %d thread(s) chosen by calibration %s ms on %d tris "
+    sample = ("first %d of %d triangles of the workload per step, whole %d^3 grid; %d thread(s) chosen by calibration %s ms on %d tris "
               "(host has %d hardware threads; the reference's global omp critical makes more threads slower)"
-              % (n_sample, len(faces), threads, cal, n_cal, max_thr))
+              % (n_sample, len(faces), w["G"], threads, cal, n_cal, max_thr))
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "Mtri/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
