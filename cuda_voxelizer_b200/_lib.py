@@ -20,7 +20,7 @@ EXPORTS = [
     "voxb200_partition", "voxb200_morton_encode", "voxb200_malloc", "voxb200_free", "voxb200_memcpy_d2h",
     "voxb200_upload_soup", "voxb200_upload_indexed", "voxb200_surface", "voxb200_solid", "voxb200_voxelize_host",
     "voxb200_launch_count", "voxb200_last_counters", "voxb200_version", "voxb200_set_profiling", "voxb200_phase_ms",
-    "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release",
+    "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release", "voxb200_sort_triangles",
 ]
 
 
@@ -80,6 +80,7 @@ def lib():
         fn.argtypes = [C.POINTER(Grid), C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(Region), C.c_void_p]
     L.voxb200_voxelize_host.argtypes = [C.POINTER(Grid), C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(Region), f3]
     L.voxb200_route_triangles.argtypes = [C.POINTER(Grid), C.c_void_p, C.c_uint, C.POINTER(Region), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p]
+    L.voxb200_sort_triangles.argtypes = [C.POINTER(Grid), C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]
     L.voxb200_voxelize_host_indexed.argtypes = [C.POINTER(Grid), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_uint, C.POINTER(Region), f3]
     L.voxb200_route_triangles_multi.argtypes = [C.POINTER(Grid), C.c_void_p, C.c_uint, C.POINTER(Region), C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.c_void_p]
     L.voxb200_extract_voxels.argtypes = [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p]

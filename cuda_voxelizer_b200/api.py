@@ -186,6 +186,14 @@ def route_triangles(grid, tris, region, solid=False, morton=False, stream=0):
     return DeviceBuffer(out.value, n.value * 36), int(n.value)
 
 
+def sort_triangles(grid, tris, stream=None):
+    """Upload-path option: a copy of the device soup (CUDA float32 tensor / DeviceBuffer, 9 floats per triangle) ordered by
+    the z-layer of each triangle's lowest vertex.  Returns a DeviceBuffer."""
+    out = C.c_void_p(0)
+    check(_lib.lib().voxb200_sort_triangles(C.byref(grid), C.c_void_p(tris.data_ptr()), C.byref(out), _stream_ptr(stream)))
+    return DeviceBuffer(out.value, int(grid.n_triangles) * 36)
+
+
 def voxelize_host_indexed(grid, host_verts, host_faces, host_table=None, solid=False, morton=False, region=None):
     """End to end from the indexed mesh (numpy or pinned torch CPU tensors): H2D of vertices + faces, expansion on the
     GPU, voxelization, D2H.  Returns (table, timing_ms[h2d+expand, voxelize, d2h, total])."""

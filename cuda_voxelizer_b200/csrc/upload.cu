@@ -214,6 +214,56 @@ cudaError_t launch_route_scatter(unsigned long long n_tris, int n_regions, const
 	return cudaGetLastError();
 }
 
+// Layer sort (upload path).  A soup that will be voxelized more than once is worth ordering by the z-layer of each
+// triangle's lowest vertex: the per-triangle kernel's atomics then sweep the table front to back (z is the slowest
+// index of the linear order), the sectors they touch are fetched once and stay in L2, and the DRAM read-modify-write
+// that otherwise costs a third of the kernel disappears (10M triangles @2048^3: 0.496 -> 0.356 ms, same table bits:
+// OR / XOR do not depend on the triangle order).  Counting sort: key + histogram, scan, scatter; the order inside a
+// layer is whatever the atomics make it.
+__global__ void __launch_bounds__(kUpBlock) layer_key_kernel(const GridParams g, const float* __restrict__ soup, unsigned int* __restrict__ keys,
+                                                             unsigned int* __restrict__ hist) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * kUpBlock + threadIdx.x;
+	if (i >= g.n_tris) return;
+	const float* p = soup + 9ull * i;
+	const float zmin = fminf(__ldg(p + 2), fminf(__ldg(p + 5), __ldg(p + 8)));
+	const float q = (zmin - g.bz) * g.ruz;                         // ordering only: any monotone key will do
+	const unsigned int key = (unsigned int)max(0, min(g.G - 1, q > 0.0f ? __float2int_rd(q) : 0));
+	keys[i] = key;
+	const unsigned int peers = __match_any_sync(__activemask(), key);
+	if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(hist + key, (unsigned int)__popc(peers));
+}
+__global__ void layer_scan_kernel(unsigned int* __restrict__ hist, int n) {          // counts -> exclusive offsets, in place
+	if (blockIdx.x != 0 || threadIdx.x != 0) return;
+	unsigned int run = 0u;
+	for (int k = 0; k < n; k++) { const unsigned int c = hist[k]; hist[k] = run; run += c; }
+}
+__global__ void __launch_bounds__(kUpBlock) layer_scatter_kernel(unsigned long long n_tris, const float* __restrict__ soup, const unsigned int* __restrict__ keys,
+                                                                 unsigned int* __restrict__ cursor, float* __restrict__ out) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * kUpBlock + threadIdx.x;
+	if (i >= n_tris) return;
+	const unsigned int key = keys[i];
+	const unsigned int peers = __match_any_sync(__activemask(), key);
+	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+	unsigned int base = 0u;
+	if (lane == leader) base = atomicAdd(cursor + key, (unsigned int)__popc(peers));
+	base = __shfl_sync(peers, base, leader);
+	const float* p = soup + 9ull * i;
+	float* o = out + 9ull * ((unsigned long long)base + __popc(peers & ((1u << lane) - 1u)));
+#pragma unroll
+	for (int k = 0; k < 9; k++) o[k] = __ldg(p + k);
+}
+
+cudaError_t launch_layer_sort(const GridParams& g, const float* d_soup, float* d_out, unsigned int* d_keys, unsigned int* d_hist, cudaStream_t st) {
+	cudaError_t e = cudaMemsetAsync(d_hist, 0, (size_t)g.G * sizeof(unsigned int), st);
+	if (e != cudaSuccess || g.n_tris == 0) return e;
+	const unsigned int blocks = (unsigned int)((g.n_tris + kUpBlock - 1) / kUpBlock);
+	layer_key_kernel<<<blocks, kUpBlock, 0, st>>>(g, d_soup, d_keys, d_hist);
+	layer_scan_kernel<<<1, 32, 0, st>>>(d_hist, g.G);
+	layer_scatter_kernel<<<blocks, kUpBlock, 0, st>>>(g.n_tris, d_soup, d_keys, d_hist, d_out);
+	g_launch_count += 3;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st) {
 	cudaError_t err = cudaMemsetAsync(d_cursor, 0, sizeof(unsigned long long), st);
 	if (err != cudaSuccess || g.n_tris == 0) return err;

@@ -471,6 +471,31 @@ int voxb200_route_triangles(const voxb200_grid* grid, const float* d_tris9, unsi
 	return VOXB200_OK;
 }
 
+int voxb200_sort_triangles(const voxb200_grid* grid, const float* d_tris9, float** d_sorted9, void* stream) {
+	if (!grid || !d_sorted9 || (!d_tris9 && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
+	if (grid->n_triangles > 0xfffffffeull) return fail(VOXB200_EINVAL, "more than 2^32 triangles");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	GridParams g;
+	size_t region_words = 0;
+	rc = resolve_region(grid, nullptr, false, &g, &region_words);
+	if (rc) return rc;
+	cudaStream_t st = (cudaStream_t)stream;
+	float* out = nullptr;
+	unsigned int *keys = nullptr, *hist = nullptr;
+	cudaError_t e = cudaMalloc(&out, grid->n_triangles ? grid->n_triangles * 9 * sizeof(float) : 16);
+	if (e == cudaSuccess) e = cudaMalloc(&keys, grid->n_triangles ? grid->n_triangles * sizeof(unsigned int) : 16);
+	if (e == cudaSuccess) e = cudaMalloc(&hist, (size_t)g.G * sizeof(unsigned int));
+	if (e == cudaSuccess) e = launch_layer_sort(g, d_tris9, out, keys, hist, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);            // the scratch below is freed on return
+	if (keys) cudaFree(keys);
+	if (hist) cudaFree(hist);
+	if (e != cudaSuccess) { if (out) cudaFree(out); return fail_cuda(e, "voxb200_sort_triangles"); }
+	*d_sorted9 = out;
+	return VOXB200_OK;
+}
+
 int voxb200_route_triangles_multi(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* regions,
                                   int n_regions, float* d_out, size_t out_capacity, size_t* counts, void* stream) {
 	if (!grid || !regions || !counts || (!d_tris9 && grid->n_triangles) || (!d_out && out_capacity)) return fail(VOXB200_EINVAL, "NULL pointer");

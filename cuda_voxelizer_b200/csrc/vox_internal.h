@@ -88,6 +88,8 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris
 cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tris, cudaStream_t st);
 cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t n_verts,
                                   bool soa4, float* d_out, cudaStream_t st);
+// Upload-path layer sort: d_out = d_soup ordered by the z-layer of each triangle's lowest vertex (d_keys: n_tris words, d_hist: G words of scratch)
+cudaError_t launch_layer_sort(const GridParams& g, const float* d_soup, float* d_out, unsigned int* d_keys, unsigned int* d_hist, cudaStream_t st);
 cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st);
 cudaError_t launch_route_count(const GridParams& g, bool solid, const int (*lo)[3], const int (*hi)[3], int n_regions, const float* d_soup,
                                unsigned int* d_masks, unsigned long long* d_counts, cudaStream_t st);

@@ -13,6 +13,9 @@ name, G = (sys.argv[1], int(sys.argv[2])) if len(sys.argv) > 2 else ("icosphere:
 slab_counts = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 8, 16, 32]
 v, f = cases.mesh(name)
 soup = np.ascontiguousarray(v[f.reshape(-1)].reshape(-1, 9))
+if os.environ.get("ZSORT"):
+    # experiment: triangles ordered by the z of their lowest vertex (what an upload-time sort would produce)
+    soup = np.ascontiguousarray(soup[np.argsort(soup[:, 2::3].min(axis=1), kind="stable")])
 d = torch.from_numpy(soup).cuda()
 T = len(f)
 grid = vb.grid_from_verts(v, G, T)

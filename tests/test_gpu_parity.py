@@ -370,6 +370,29 @@ def test_cuda_graph_capture_and_replay(vb, solid):
         assert torch.equal(table, want)
 
 
+@pytest.mark.parametrize("name,g", [("bunny", 256), ("icosphere:64:128", 256), ("soup:mixed:3000:5:1.0", 128)])
+def test_sort_triangles_keeps_the_table(vb, name, g):
+    """voxb200_sort_triangles (upload-path option) permutes the soup by z-layer: same multiset of triangles, lowest-vertex z
+    layers non-decreasing, and — OR / XOR being order-independent — bit-identical surface and solid tables."""
+    v, f, d_tris = _device_mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    buf = vb.sort_triangles(grid, d_tris)
+    torch.cuda.synchronize()
+    host = vb.download(buf.ptr, d_tris.numel() * 4).view(np.float32).reshape(-1, 9)
+    orig = d_tris.cpu().numpy().reshape(-1, 9)
+    key = lambda a: a[np.lexsort(a.T[::-1])]
+    assert np.array_equal(key(host), key(orig)), "the sorted soup is not a permutation of the input"
+    layer = np.clip(np.floor((host[:, 2::3].min(axis=1) - np.float32(grid.bbox_min[2])) * (np.float32(1.0) / np.float32(grid.unit[2]))), 0, g - 1)
+    assert np.all(np.diff(layer) >= 0)
+    d_sorted = torch.from_numpy(host.reshape(-1)).cuda()
+    for solid in (0, 1):
+        if solid and name.startswith("soup"):
+            continue
+        fn = vb.voxelize_solid if solid else vb.voxelize
+        assert torch.equal(fn(grid, d_sorted), fn(grid, d_tris))
+    buf.close()
+
+
 def test_queue_unit_overflow_is_reported(vb):
     """The large-triangle queue counts its work units ((y,z) rows) in 32 bits.  A soup that queues more than 2^32 rows in
     one call must be reported (last_counters, and an error from the synchronous host entry point), not silently mangled."""
