@@ -141,6 +141,13 @@ def test_compute_fails_loudly_without_gpu(vb):
         vb.voxelize_host(grid, tris, table)
     assert e.value.code == _lib.ENODEVICE
 
+    class FakeDeviceSoup:           # any pointer will do: the call must stop at the device check
+        def data_ptr(self):
+            return tris.ctypes.data
+    with pytest.raises(vb.VoxError) as e:
+        vb.sort_triangles(grid, FakeDeviceSoup(), stream=0)
+    assert e.value.code == _lib.ENODEVICE
+
 
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "cuda_voxelizer_b200")
