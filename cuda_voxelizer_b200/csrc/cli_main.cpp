@@ -28,6 +28,7 @@ struct Options {
 	bool force_cpu = false;
 	bool solid = false;
 	std::string from_table;    // test hook: skip the GPU, read a raw linear bit table from this file and only run the writer
+	std::string dump_mesh;     // test hook: write the loaded mesh (u64 nv, u64 nf, float32 xyz[nv], int32 abc[nf]) to this file and exit
 };
 
 void print_help() {
@@ -72,6 +73,8 @@ Options parse(int argc, char* argv[]) {
 			o.solid = true;
 		} else if (a == "--from-table" && i + 1 < argc) {
 			o.from_table = argv[++i];
+		} else if (a == "--dump-mesh" && i + 1 < argc) {
+			o.dump_mesh = argv[++i];
 		}
 	}
 	if (!have_file) { printf("[Err] You didn't specify a file using -f (path). This is required. Exiting. \n"); exit(1); }
@@ -107,6 +110,16 @@ int main(int argc, char* argv[]) {
 	printf("[Mesh] Number of triangles: %zu \n", mesh.n_faces());
 	printf("[Mesh] Number of vertices: %zu \n", mesh.n_vertices());
 	printf("[Mesh] Computing bbox \n");
+	if (!opt.dump_mesh.empty()) {
+		FILE* df = fopen(opt.dump_mesh.c_str(), "wb");
+		if (!df) { printf("[Err] cannot write %s \n", opt.dump_mesh.c_str()); return 1; }
+		const unsigned long long counts[2] = {mesh.n_vertices(), mesh.n_faces()};
+		fwrite(counts, sizeof(counts), 1, df);
+		fwrite(mesh.vertices.data(), sizeof(float), mesh.vertices.size(), df);
+		fwrite(mesh.faces.data(), sizeof(int32_t), mesh.faces.size(), df);
+		fclose(df);
+		return 0;
+	}
 
 	printf("\n## VOXELISATION SETUP \n");
 	voxb200_grid grid;

@@ -1,11 +1,22 @@
 // mesh_io.cpp — mesh loading for the CLI (stands in for trimesh2's TriMesh::read + need_faces + need_bbox,
-// main.cpp:174-179).  Floats are parsed with strtof, i.e. correctly rounded binary32 like trimesh2's sscanf("%f").
+// main.cpp:174-179).  Floats are parsed with strtof / std::from_chars, i.e. correctly rounded binary32 like trimesh2's
+// sscanf("%f").  OBJ files — where ingest dominates once the voxelization takes a millisecond — are
+// memory-mapped and parsed by all host threads at once (chunks cut at line ends, relative indices resolved after a
+// prefix sum of the chunks' vertex counts); the line-by-line parser stays as the fallback and as the reference the
+// parallel one is tested against (VOXCLI_SERIAL_LOADER=1).
 #include <cerrno>
+#include <charconv>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <thread>
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "cli.h"
 
@@ -51,6 +62,117 @@ bool load_obj(const std::string& path, Mesh& m, std::string& error) {
 		}
 	}
 	fclose(f);
+	return true;
+}
+
+// ---- parallel OBJ parser ----------------------------------------------------------------------
+inline bool is_blank(char c) { return c == ' ' || c == '\t'; }
+inline bool is_eol(char c) { return c == '\n' || c == '\r'; }
+
+// strtof's result on [p, end): correctly rounded binary32.  from_chars takes no leading '+' and no hex floats; anything it
+// does not take goes through strtof on a bounded copy.  `p` advances past the number (or stays when there is none).
+float parse_float(const char*& p, const char* end) {
+	while (p < end && is_blank(*p)) p++;
+	const char* q = p;
+	if (q < end && *q == '+') q++;
+	float v = 0.0f;
+	const auto r = std::from_chars(q, end, v);
+	if (r.ec == std::errc() && !(r.ptr < end && (*r.ptr == 'x' || *r.ptr == 'X'))) { p = r.ptr; return v; }
+	char buf[128];
+	size_t n = 0;
+	while (p + n < end && n + 1 < sizeof(buf) && !is_eol(p[n])) { buf[n] = p[n]; n++; }
+	buf[n] = '\0';
+	char* e;
+	v = strtof(buf, &e);
+	p += e - buf;
+	return v;
+}
+
+struct ObjChunk {
+	std::vector<float> vertices;
+	std::vector<int32_t> faces;              // 0-based, or (for relative indices, written <= 0) the written value minus one
+	std::vector<std::pair<size_t, int32_t>> relative;      // {position in faces, vertices of this chunk seen before that face}
+};
+
+void parse_obj_chunk(const char* p, const char* end, ObjChunk& c) {
+	std::vector<int32_t> poly;
+	while (p < end) {
+		const char* line_end = static_cast<const char*>(memchr(p, '\n', (size_t)(end - p)));
+		if (!line_end) line_end = end;
+		const char* q = p;
+		while (q < line_end && is_blank(*q)) q++;
+		if (q + 1 < line_end && q[0] == 'v' && is_blank(q[1])) {
+			q++;
+			for (int k = 0; k < 3; k++) c.vertices.push_back(parse_float(q, line_end));
+		} else if (q + 1 < line_end && q[0] == 'f' && is_blank(q[1])) {
+			q++;
+			poly.clear();
+			const int32_t seen = (int32_t)(c.vertices.size() / 3);
+			for (;;) {
+				while (q < line_end && is_blank(*q)) q++;
+				if (q >= line_end || is_eol(*q)) break;
+				const char* d = q;
+				if (d < line_end && *d == '+') d++;
+				long idx = 0;
+				const auto r = std::from_chars(d, line_end, idx);
+				if (r.ec != std::errc()) break;
+				poly.push_back((int32_t)(idx - 1));      // idx <= 0 (stored < 0): relative to the vertices read so far, resolved by the caller
+				q = r.ptr;
+				while (q < line_end && !is_blank(*q) && !is_eol(*q)) q++;   // skip /t/n
+			}
+			for (size_t k = 1; k + 1 < poly.size(); k++)
+				for (int32_t idx : {poly[0], poly[k], poly[k + 1]}) {
+					if (idx < 0) c.relative.emplace_back(c.faces.size(), seen);
+					c.faces.push_back(idx);
+				}
+		}
+		p = line_end + 1;
+	}
+}
+
+bool load_obj_parallel(const std::string& path, Mesh& m, std::string& error) {
+	const int fd = open(path.c_str(), O_RDONLY);
+	if (fd < 0) { error = "cannot open " + path; return false; }
+	struct stat st;
+	if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); return load_obj(path, m, error); }
+	const size_t size = (size_t)st.st_size;
+	void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+	close(fd);
+	if (map == MAP_FAILED) return load_obj(path, m, error);
+	const char* base = static_cast<const char*>(map);
+	unsigned int n_threads = std::thread::hardware_concurrency();
+	if (n_threads == 0) n_threads = 1;
+	if (n_threads > 32) n_threads = 32;
+	if (const char* env = getenv("VOXCLI_LOADER_THREADS")) { const int want = atoi(env); if (want >= 1 && want <= 256) n_threads = (unsigned int)want; }
+	if (size < (size_t(1) << 20)) n_threads = 1;
+	// chunk starts: byte offsets moved forward to the character after the next newline
+	std::vector<size_t> cut(n_threads + 1, size);
+	cut[0] = 0;
+	for (unsigned int t = 1; t < n_threads; t++) {
+		size_t at = size / n_threads * t;
+		const char* nl = static_cast<const char*>(memchr(base + at, '\n', size - at));
+		cut[t] = nl ? (size_t)(nl - base) + 1 : size;
+		if (cut[t] < cut[t - 1]) cut[t] = cut[t - 1];
+	}
+	std::vector<ObjChunk> chunks(n_threads);
+	std::vector<std::thread> pool;
+	for (unsigned int t = 1; t < n_threads; t++) pool.emplace_back([&, t] { parse_obj_chunk(base + cut[t], base + cut[t + 1], chunks[t]); });
+	parse_obj_chunk(base + cut[0], base + cut[1], chunks[0]);
+	for (auto& th : pool) th.join();
+	munmap(map, size);
+	size_t nv3 = 0, nf3 = 0;
+	for (auto& c : chunks) { nv3 += c.vertices.size(); nf3 += c.faces.size(); }
+	m.vertices.resize(nv3);
+	m.faces.resize(nf3);
+	size_t v_at = 0, f_at = 0;
+	for (auto& c : chunks) {
+		// relative (negative / zero) indices count back from the vertices read so far — in the whole file
+		for (auto& rel : c.relative) c.faces[rel.first] = (int32_t)((long)(v_at / 3) + rel.second + c.faces[rel.first] + 1);
+		if (!c.vertices.empty()) memcpy(m.vertices.data() + v_at, c.vertices.data(), c.vertices.size() * sizeof(float));
+		if (!c.faces.empty()) memcpy(m.faces.data() + f_at, c.faces.data(), c.faces.size() * sizeof(int32_t));
+		v_at += c.vertices.size();
+		f_at += c.faces.size();
+	}
 	return true;
 }
 
@@ -129,7 +251,8 @@ bool load_mesh(const std::string& path, Mesh& m, std::string& error) {
 	std::string ext = path.substr(path.find_last_of('.') == std::string::npos ? path.size() : path.find_last_of('.') + 1);
 	for (auto& c : ext) c = (char)tolower(c);
 	bool ok;
-	if (ext == "obj") ok = load_obj(path, m, error);
+	const char* serial = getenv("VOXCLI_SERIAL_LOADER");
+	if (ext == "obj") ok = (serial && serial[0] == '1') ? load_obj(path, m, error) : load_obj_parallel(path, m, error);
 	else if (ext == "ply") ok = load_ply(path, m, error);
 	else { error = "unsupported mesh format ." + ext + " (this build reads .obj and .ply; trimesh2 is not linked)"; return false; }
 	if (!ok) return false;

@@ -70,3 +70,62 @@ def test_flags_without_gpu(work):
     assert r.returncode == 1 and "Unrecognized output format" in r.stdout
     r = _run(["-f", work["obj"], "-s", "64", "-cpu"])
     assert r.returncode == 1 and "no CPU voxelization path" in r.stdout
+
+
+def _dump(path, out, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    r = subprocess.run([CLI, "-f", path, "-s", "64", "--dump-mesh", out], capture_output=True, text=True, timeout=300, env=e)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = open(out, "rb").read()
+    nv, nf = np.frombuffer(raw[:16], np.uint64)
+    v = np.frombuffer(raw[16:16 + 12 * int(nv)], np.float32).reshape(-1, 3)
+    f = np.frombuffer(raw[16 + 12 * int(nv):], np.int32).reshape(-1, 3)
+    assert len(f) == nf
+    return v, f
+
+
+def test_parallel_obj_loader_matches_the_line_by_line_parser(work, tmp_path):
+    """The memory-mapped, multi-threaded OBJ parser (ingest) against the fgets/strtof one it replaces, bit for
+    bit: number formats, '+' signs, CRLF, comments, vn/vt lines, a/t/n index forms, polygons, relative indices across
+    chunk boundaries, at several thread counts (the file is > 1 MB so that it really is cut into chunks)."""
+    rng = np.random.default_rng(7)
+    lines = ["# header comment", "mtllib x.mtl", "o thing"]
+    n_blocks = 5000
+    for b in range(n_blocks):
+        for k in range(4):
+            x, y, z = rng.normal(0, 10, 3)
+            fmt = ("v %.9g %.9g %.9g", "v %+.7e %.3f %.12g 1.0", "v\t%f  %g %.1f 0.5 0.25 0.125", "  v %.9g %.9g %.9g")[(b + k) % 4]
+            lines.append(fmt % (x, y, z))
+        lines.append("vn 0 0 1")
+        lines.append("vt 0.5 0.5")
+        base = 4 * b + 1
+        form = b % 5
+        if form == 0:
+            lines.append("f %d %d %d" % (base, base + 1, base + 2))
+        elif form == 1:
+            lines.append("f %d/1/1 %d/1/1 %d/1/1 %d/1/1" % (base, base + 1, base + 2, base + 3))        # a quad: fanned
+        elif form == 2:
+            lines.append("f %d//1 %d//1 %d//1" % (base + 3, base + 2, base + 1))
+        elif form == 3:
+            lines.append("f -4 -3 -2")                                                                  # relative to the vertices read so far
+        else:
+            lines.append("f -1/1 -2/1 -3/1 -4/1")
+        if b % 97 == 0:
+            lines.append("")
+            lines.append("# " + "x" * 3000)                                                             # a long comment line
+    text = "\n".join(lines) + "\n"
+    assert len(text) > (1 << 20)
+    unix, dos = str(tmp_path / "mix.obj"), str(tmp_path / "mix_crlf.obj")
+    open(unix, "w").write(text)
+    open(dos, "w", newline="").write(text.replace("\n", "\r\n"))
+    ref_v, ref_f = _dump(unix, str(tmp_path / "ref.bin"), {"VOXCLI_SERIAL_LOADER": "1"})
+    assert len(ref_v) == 4 * n_blocks and ref_f.min() >= 0 and ref_f.max() < len(ref_v)
+    for path in (unix, dos):
+        for threads in ("1", "2", "3", "8", "31"):
+            v, f = _dump(path, str(tmp_path / "par.bin"), {"VOXCLI_LOADER_THREADS": threads})
+            assert v.tobytes() == ref_v.tobytes() and f.tobytes() == ref_f.tobytes(), (path, threads)
+    # and the bundled bunny, against the arrays the file was written from
+    v, f = _dump(work["obj"], str(tmp_path / "bunny.bin"))
+    bv, bf = cases.mesh("bunny")
+    assert np.array_equal(v, bv) and np.array_equal(f, bf)
