@@ -91,14 +91,49 @@ void write_binvox(const VoxelList& vox, const voxinfo& info, const std::string& 
 	out.write(buf.data(), (std::streamsize)buf.size());
 }
 
+// Text output without a printf per line: decimal digits appended to a 4 MB buffer (the fprintf version spent 1.2 s on
+// the 3.5 M points of bunny@1024^3, and ten times that on the cube mesh).
+namespace {
+struct TextOut {
+	FILE* f;
+	std::vector<char> buf;
+	size_t n = 0;
+	explicit TextOut(FILE* file) : f(file), buf(size_t(4) << 20) {}
+	void room(size_t bytes) { if (n + bytes > buf.size()) flush(); }
+	void flush() { if (n) fwrite(buf.data(), 1, n, f); n = 0; }
+	void put(char c) { buf[n++] = c; }
+	void put(const char* s, size_t len) { memcpy(buf.data() + n, s, len); n += len; }
+	void put_uint(unsigned long v) {
+		char tmp[24];
+		int k = 0;
+		do { tmp[k++] = (char)('0' + v % 10); v /= 10; } while (v);
+		while (k) buf[n++] = tmp[--k];
+	}
+};
+}  // namespace
+
 void write_obj_pointcloud(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
 	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + "_pointcloud.obj";
 	fprintf(stdout, "[I/O] Writing data in obj point cloud format to %s \n", name.c_str());
 	FILE* out = fopen(name.c_str(), "w");
 	if (!out) return;
 	const uint64_t G = vox.gridsize;
-	for (uint64_t k : traversal_keys(vox, Axis::x, Axis::y, Axis::z))      // x -> y -> z like util_io.cpp:167-181
-		fprintf(out, "v %g %g %g\n", (double)(k / (G * G)) + 0.5, (double)((k / G) % G) + 0.5, (double)(k % G) + 0.5);   // %g == ostream default
+	const std::vector<uint64_t> keys = traversal_keys(vox, Axis::x, Axis::y, Axis::z);      // x -> y -> z like util_io.cpp:167-181
+	if (G <= 99999) {
+		// the reference streams (coordinate + 0.5) with ostream's default format, i.e. %g: for coordinates below 10^5 that is
+		// the integer followed by ".5" (at most 6 significant digits, nothing to round or trim)
+		TextOut t(out);
+		for (uint64_t k : keys) {
+			t.room(64);
+			t.put('v'); t.put(' '); t.put_uint((unsigned long)(k / (G * G))); t.put(".5 ", 3);
+			t.put_uint((unsigned long)((k / G) % G)); t.put(".5 ", 3);
+			t.put_uint((unsigned long)(k % G)); t.put(".5\n", 3);
+		}
+		t.flush();
+	} else {
+		for (uint64_t k : keys)
+			fprintf(out, "v %g %g %g\n", (double)(k / (G * G)) + 0.5, (double)((k / G) % G) + 0.5, (double)(k % G) + 0.5);   // %g == ostream default
+	}
 	fclose(out);
 }
 
@@ -111,12 +146,19 @@ void write_obj_cubes(const VoxelList& vox, const voxinfo& info, const std::strin
 	static const int corner[8][3] = {{1, 1, 0}, {0, 1, 0}, {1, 0, 0}, {0, 0, 0}, {0, 0, 1}, {1, 0, 1}, {0, 1, 1}, {1, 1, 1}};   // v8..v1
 	static const int face[12][3] = {{-1, -3, -4}, {-1, -4, -2}, {-4, -3, -6}, {-4, -6, -5}, {-3, -1, -8}, {-3, -8, -6},
 	                                {-1, -2, -7}, {-1, -7, -8}, {-2, -4, -5}, {-2, -5, -7}, {-5, -6, -8}, {-5, -8, -7}};
+	std::string faces;                                          // the twelve face lines are the same text for every cube
+	for (const auto& f : face) faces += "f " + std::to_string(f[0]) + " " + std::to_string(f[1]) + " " + std::to_string(f[2]) + "\n";
 	const uint64_t G = vox.gridsize;
+	TextOut t(out);
 	for (uint64_t k : traversal_keys(vox, Axis::x, Axis::y, Axis::z)) {
-		const long x = (long)(k / (G * G)), y = (long)((k / G) % G), z = (long)(k % G);
-		for (const auto& c : corner) fprintf(out, "v %ld %ld %ld\n", x + c[0], y + c[1], z + c[2]);
-		for (const auto& f : face) fprintf(out, "f %d %d %d\n", f[0], f[1], f[2]);
+		const unsigned long x = (unsigned long)(k / (G * G)), y = (unsigned long)((k / G) % G), z = (unsigned long)(k % G);
+		t.room(8 * 80 + faces.size());
+		for (const auto& c : corner) {
+			t.put('v'); t.put(' '); t.put_uint(x + (unsigned long)c[0]); t.put(' '); t.put_uint(y + (unsigned long)c[1]); t.put(' '); t.put_uint(z + (unsigned long)c[2]); t.put('\n');
+		}
+		t.put(faces.data(), faces.size());
 	}
+	t.flush();
 	fclose(out);
 }
 
