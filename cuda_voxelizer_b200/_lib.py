@@ -21,6 +21,7 @@ EXPORTS = [
     "voxb200_upload_soup", "voxb200_upload_indexed", "voxb200_surface", "voxb200_solid", "voxb200_voxelize_host",
     "voxb200_launch_count", "voxb200_last_counters", "voxb200_version", "voxb200_set_profiling", "voxb200_phase_ms",
     "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release", "voxb200_sort_triangles",
+    "voxb200_reference_table_bytes",
 ]
 
 
@@ -68,6 +69,8 @@ def lib():
     L.voxb200_make_grid.argtypes = [f3, f3, C.c_uint, C.c_size_t, C.POINTER(Grid)]
     L.voxb200_table_bytes.argtypes = [C.c_uint]
     L.voxb200_table_bytes.restype = C.c_size_t
+    L.voxb200_reference_table_bytes.argtypes = [C.c_uint]
+    L.voxb200_reference_table_bytes.restype = C.c_size_t
     L.voxb200_partition.argtypes = [C.c_uint, C.c_int, C.c_int, C.c_int, C.POINTER(Region), C.POINTER(C.c_size_t)]
     L.voxb200_morton_encode.argtypes = [C.c_uint, C.c_uint, C.c_uint]
     L.voxb200_morton_encode.restype = C.c_uint64

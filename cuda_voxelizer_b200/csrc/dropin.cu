@@ -29,12 +29,27 @@ void run(bool solid, const voxinfo& v, float* triangle_data, unsigned int* vtabl
 	if (cudaEventCreate(&start_vox) != cudaSuccess || cudaEventCreate(&stop_vox) != cudaSuccess) die("cudaEventCreate", VOXB200_ECUDA);
 	const unsigned int flags = (morton_code ? VOXB200_MORTON : 0u) | VOXB200_ACCUMULATE;
 	const voxb200_grid* grid = reinterpret_cast<const voxb200_grid*>(&v);
+	// The caller sized vtable with the reference's formula (main.cpp:190), which is a word short of G^3 bits for some odd
+	// grid sizes; the reference's kernels then write past it.  Here such a grid is voxelized in a library-owned table of the
+	// full size and the caller's bytes are copied back, so nothing is written outside the caller's allocation.
+	const size_t have = voxb200_reference_table_bytes(v.gridsize.x), need = voxb200_table_bytes(v.gridsize.x);
+	unsigned int* work = vtable;
+	if (need > have) {
+		void* p = nullptr;
+		if (int rc = voxb200_malloc(&p, need)) die("voxb200_malloc", rc);
+		work = static_cast<unsigned int*>(p);
+		if (cudaMemset(work, 0, need) != cudaSuccess || cudaMemcpy(work, vtable, have, cudaMemcpyDefault) != cudaSuccess) die("cudaMemcpy", VOXB200_ECUDA);
+	}
 	cudaEventRecord(start_vox, 0);
-	const int rc = solid ? voxb200_solid(grid, triangle_data, vtable, flags, nullptr, nullptr)
-	                     : voxb200_surface(grid, triangle_data, vtable, flags, nullptr, nullptr);
+	const int rc = solid ? voxb200_solid(grid, triangle_data, work, flags, nullptr, nullptr)
+	                     : voxb200_surface(grid, triangle_data, work, flags, nullptr, nullptr);
 	if (rc) die(solid ? "voxelize_solid" : "voxelize", rc);
 	cudaEventRecord(stop_vox, 0);
 	cudaError_t e = cudaDeviceSynchronize();
+	if (e == cudaSuccess && work != vtable) {
+		e = cudaMemcpy(vtable, work, have, cudaMemcpyDefault);
+		voxb200_free(work);
+	}
 	if (e != cudaSuccess) { fprintf(stderr, "CUDA error at voxelize: code=%d(%s) \n", (int)e, cudaGetErrorName(e)); exit(EXIT_FAILURE); }
 	uint64_t counters[4] = {0, 0, 0, 0};
 	if (voxb200_last_counters(counters) != VOXB200_OK) die("voxb200_last_counters", VOXB200_ECUDA);

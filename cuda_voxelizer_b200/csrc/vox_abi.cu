@@ -327,10 +327,21 @@ int voxb200_make_grid(const float mesh_min[3], const float mesh_max[3], unsigned
 	return VOXB200_OK;
 }
 
-// main.cpp:190 — ceil(G^3 / 32.0f) * 4 with the reference's float division
-size_t voxb200_table_bytes(unsigned int gridsize) {
+// main.cpp:190 — ceil(G^3 / 32.0f) * 4 with the reference's float division.  Above 2^24 voxels the conversion of G^3 to
+// binary32 can round DOWN, and the reference's table then holds fewer than G^3 bits (629 of the grid sizes 1..2048, none
+// of them a multiple of 32: G = 257, 513, 1025 are one bit short, G = 1026 eight): its far-corner voxels index the word one
+// past the allocation.  A size API must not hand out a table the kernels can overrun, so this returns the larger of the
+// reference's value and the exact ceil(G^3 / 32) * 4; voxb200_reference_table_bytes() keeps the reference's own number
+// for callers (the C++ drop-in symbols) whose buffer was sized by the reference's main().
+size_t voxb200_reference_table_bytes(unsigned int gridsize) {
 	const size_t g = gridsize;
 	return static_cast<size_t>(ceil((g * g * g) / 32.0f) * 4);
+}
+size_t voxb200_table_bytes(unsigned int gridsize) {
+	const size_t g = gridsize;
+	const size_t exact = ((g * g * g + 31) / 32) * 4;
+	const size_t ref = voxb200_reference_table_bytes(gridsize);
+	return exact > ref ? exact : ref;
 }
 
 uint64_t voxb200_morton_encode(unsigned int x, unsigned int y, unsigned int z) { return morton3(x, y, z); }

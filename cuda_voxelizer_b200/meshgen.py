@@ -142,3 +142,13 @@ def random_soup(n, seed, extent=1.0, kind="mixed"):
     verts = tri.reshape(-1, 3).astype(np.float32)
     faces = np.arange(3 * len(tri), dtype=np.int32).reshape(-1, 3)
     return verts, faces
+
+
+def box(extent=1.0):
+    """Axis-aligned cube [0, extent]^3 as 12 outward-CCW triangles (8 shared vertices).  Its far corner lands in voxel
+    (G-1, G-1, G-1): the mesh that exercises the last bit of the table."""
+    e = float(extent)
+    v = np.array([[x, y, z] for z in (0.0, e) for y in (0.0, e) for x in (0.0, e)], np.float32)
+    f = np.array([[0, 2, 1], [1, 2, 3], [4, 5, 6], [5, 7, 6], [0, 1, 4], [1, 5, 4],
+                  [2, 6, 3], [3, 6, 7], [0, 4, 2], [2, 4, 6], [1, 3, 5], [3, 7, 5]], np.int32)
+    return v, f

@@ -90,7 +90,12 @@ const char* voxb200_last_error(void);
 /* mesh_min/mesh_max: bbox over all mesh vertices.  Cube-ifies, pads by 1/10001, derives unit. */
 int voxb200_make_grid(const float mesh_min[3], const float mesh_max[3], unsigned int gridsize,
                       size_t n_triangles, voxb200_grid* out);
+/* Bytes of a whole table: max(the reference's ceil(G^3/32.0f)*4, the exact ceil(G^3/32)*4).  The two agree for every G that is a
+ * multiple of 32 (all fast paths, morton order); for 629 odd sizes below 2048 the reference's binary32 division comes out a
+ * word short and its own kernels write past the table (main.cpp:190) — size tables with THIS function.
+ * voxb200_reference_table_bytes is the reference's number, for buffers that were sized by the reference's main(). */
 size_t voxb200_table_bytes(unsigned int gridsize);
+size_t voxb200_reference_table_bytes(unsigned int gridsize);
 /* Region rank `part` of `n_parts` (n_parts a power of two <= 8 for morton; any n <= gridsize for
  * linear).  Writes the region and its size in bytes. */
 int voxb200_partition(unsigned int gridsize, int morton, int part, int n_parts,

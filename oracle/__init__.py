@@ -5,6 +5,8 @@ ctypes access to the two CPU checkers:
 * ``liboracle.so``       — oracle/vox_oracle.c, the plain-C restatement of the reference algorithm
 * ``_ref/libvoxref.so``  — the reference's own unmodified ``src/cpu_voxelizer.cpp`` compiled here
                            from /root/reference (oracle/Makefile); travels to the GPU box prebuilt
+* ``_ref/libvoxref_gpu.so`` — the reference's own unmodified GPU kernels (``src/voxelize.cu``,
+                           ``src/voxelize_solid.cu``) compiled for sm_100a: bench.py's second baseline
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference``
 legs may import this package.  ``cuda_voxelizer_b200`` never does.
@@ -52,6 +54,8 @@ def lib():
         L.oracle_unit.argtypes = [_f32p, _f32p, C.c_uint, _f32p]
         L.oracle_table_bytes.argtypes = [C.c_uint]
         L.oracle_table_bytes.restype = C.c_size_t
+        L.oracle_reference_table_bytes.argtypes = [C.c_uint]
+        L.oracle_reference_table_bytes.restype = C.c_size_t
         L.oracle_morton.argtypes = [C.c_uint, C.c_uint, C.c_uint]
         L.oracle_morton.restype = C.c_uint64
         for fn in (L.oracle_surface, L.oracle_solid):
@@ -211,3 +215,30 @@ def ref_write(fmt, table, gridsize, bbox_min, bbox_max, n_tris, base_filename):
     rc = _ref_io.voxref_write(code, np.ascontiguousarray(table, np.uint32), gridsize, np.ascontiguousarray(bbox_min, np.float32),
                               np.ascontiguousarray(bbox_max, np.float32), n_tris, base_filename.encode())
     assert rc == 0
+
+
+# ----------------------------------------------------------------------------- compiled reference GPU kernels (bench baseline)
+_REF_GPU_SO = os.path.join(_HERE, "_ref", "libvoxref_gpu.so")
+_ref_gpu = None
+
+
+def have_ref_gpu():
+    return os.path.exists(_REF_GPU_SO)
+
+
+def ref_gpu_run(bbox_min, bbox_max, gridsize, soup9, solid=False, morton=False, warmup=2, reps=5, want_table=False):
+    """Time the reference's own voxelize() / voxelize_solid() (unmodified kernels, sm_100a build) on the current CUDA
+    device with triangles and table device-resident.  Returns ({"mean_ms", "best_ms", "memset_ms"}, table or None)."""
+    global _ref_gpu
+    if _ref_gpu is None:
+        _ref_gpu = C.CDLL(_REF_GPU_SO)
+        _ref_gpu.voxrefgpu_run.argtypes = [_f32p, C.c_uint, _f32p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p]
+    soup9 = np.ascontiguousarray(soup9, np.float32).reshape(-1, 9)
+    bbox6 = np.ascontiguousarray(np.concatenate([np.asarray(bbox_min, np.float32), np.asarray(bbox_max, np.float32)]))
+    out = np.zeros(3, np.float32)
+    table = np.zeros(table_words(gridsize), np.uint32) if want_table else None
+    rc = _ref_gpu.voxrefgpu_run(bbox6, gridsize, soup9, len(soup9), int(bool(solid)), int(bool(morton)), int(warmup), int(reps), out,
+                                table.ctypes.data if table is not None else None)
+    if rc != 0:
+        raise RuntimeError("reference GPU kernels failed: CUDA error %d" % rc)
+    return {"mean_ms": float(out[0]), "best_ms": float(out[1]), "memset_ms": float(out[2])}, table

@@ -100,10 +100,17 @@ void oracle_unit(const float bb_min[3], const float bb_max[3], unsigned int grid
 	for (int k = 0; k < 3; k++) unit[k] = (bb_max[k] - bb_min[k]) / (float)gridsize;
 }
 
-/* main.cpp:190 */
-size_t oracle_table_bytes(unsigned int gridsize) {
+/* main.cpp:190 — the reference's size; its binary32 division rounds G^3 down for some odd grid sizes (G = 257: one bit
+ * short) and the reference then writes one word past its table.  The oracle's tables are sized to hold every voxel
+ * (max of both formulas) so that this out-of-bounds write of the reference lands inside the buffer and can be compared. */
+size_t oracle_reference_table_bytes(unsigned int gridsize) {
 	size_t g = gridsize;
 	return (size_t)(ceil((g * g * g) / 32.0f) * 4);
+}
+size_t oracle_table_bytes(unsigned int gridsize) {
+	size_t g = gridsize;
+	size_t exact = ((g * g * g + 31) / 32) * 4, ref = oracle_reference_table_bytes(gridsize);
+	return exact > ref ? exact : ref;
 }
 
 /* ------------------------------------------------------------------ morton (cpu_voxelizer.cpp:18-32) */

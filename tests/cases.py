@@ -37,6 +37,8 @@ def mesh(name):
     if kind == "soup":               # soup:<kind>:<n>:<seed>:<extent>
         k, n, seed, extent = arg.split(":")
         return meshgen.random_soup(int(n), int(seed), extent=float(extent), kind=k)
+    if kind == "box":                # box:<extent>
+        return meshgen.box(float(arg))
     raise KeyError(name)
 
 

@@ -77,9 +77,19 @@ def test_make_grid_golden(vb, golden):
     assert [float(x) for x in grid.bbox_min] == want["bbox_min"] and [float(x) for x in grid.unit] == want["unit"]
 
 
-@pytest.mark.parametrize("g", [1, 2, 3, 8, 31, 32, 33, 100, 256, 1024, 2048])
+@pytest.mark.parametrize("g", [1, 2, 3, 8, 31, 32, 33, 100, 256, 257, 513, 1024, 1025, 1026, 2048])
 def test_table_bytes(vb, g):
     assert vb.table_bytes(g) == oracle.lib().oracle_table_bytes(g)
+    assert vb.table_bytes(g) * 8 >= g ** 3                 # every voxel has a bit (the reference's own formula fails this at 257, 513, 1025, 1026)
+    ref = int(_lib_raw(vb).voxb200_reference_table_bytes(g))
+    assert ref == oracle.lib().oracle_reference_table_bytes(g) and vb.table_bytes(g) >= ref
+    if g % 32 == 0:
+        assert vb.table_bytes(g) == ref == g ** 3 // 8
+
+
+def _lib_raw(vb):
+    from cuda_voxelizer_b200 import _lib
+    return _lib.lib()
 
 
 def test_morton_encode_matches_oracle(vb):

@@ -78,6 +78,23 @@ def test_odd_and_tiny_grids(vb, g, solid):
     assert np.array_equal(table, want)
 
 
+@pytest.mark.parametrize("g", [257, 513])
+@pytest.mark.parametrize("solid", [0, 1])
+def test_box_reaches_the_last_table_bit(vb, g, solid):
+    """At these sizes the reference's ceil(G^3/32.0f)*4 is a bit short of G^3 voxels: voxb200_table_bytes must hold
+    the far-corner voxel, and the kernels must set it like the oracle does."""
+    name = "box:10"
+    table, grid = _run(vb, name, g, solid, 0)
+    assert table.nbytes == vb.table_bytes(g) and table.nbytes * 8 >= g ** 3
+    v, f, _ = _device_mesh(name)
+    mn, mx, unit = oracle.voxinfo(v, g)
+    want = (oracle.solid if solid else oracle.surface)(oracle.soup(v, f), mn, unit, g, 0)
+    assert np.array_equal(table, want)
+    if not solid:
+        last = g ** 3 - 1
+        assert (int(table[last // 32]) >> (31 - last % 32)) & 1 == 1
+
+
 @pytest.mark.parametrize("name,g,solid", [("bunny", 128, 0), ("bunny", 128, 1), ("icosphere:64:128", 256, 0), ("icosphere:64:128", 256, 1)])
 def test_soa4_layout_gives_same_table(vb, name, g, solid):
     v, f, d_tris = _device_mesh(name)
