@@ -243,3 +243,46 @@ def extract_voxels(table, first_voxel=0, stream=None):
 def release():
     """Free everything the library cached for the current device."""
     check(_lib.lib().voxb200_release())
+
+
+class Mesh:
+    """A mesh prepared for repeated voxelization on one grid (voxb200_mesh_*): owns its re-ordered triangles, the tile plan
+    and a private workspace.  ``tris``: CUDA float32 tensor with 9 floats per triangle, or pass ``verts`` / ``faces`` (CUDA
+    float32 [V,3] / int32 [T,3]) for an indexed mesh.  Re-entrant: meshes may voxelize concurrently on different streams."""
+
+    def __init__(self, grid, tris=None, verts=None, faces=None, solid=False, morton=False, region=None, stream=None):
+        self.grid, self.region, self.solid, self.morton = grid, region, solid, morton
+        self._h = C.c_void_p(0)
+        flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+        rp = C.byref(region) if region is not None else None
+        if tris is not None:
+            check(_lib.lib().voxb200_mesh_create(C.byref(grid), C.c_void_p(tris.data_ptr()), flags, rp, C.byref(self._h), _stream_ptr(stream)))
+        else:
+            check(_lib.lib().voxb200_mesh_create_indexed(C.byref(grid), C.c_void_p(verts.data_ptr()), verts.numel() // 3, C.c_void_p(faces.data_ptr()),
+                                                         flags, rp, C.byref(self._h), _stream_ptr(stream)))
+
+    def update(self, tris=None, verts=None, faces=None, stream=None):
+        """New vertex positions (same triangle count): re-prepares the handle in place."""
+        if tris is not None:
+            check(_lib.lib().voxb200_mesh_update(self._h, C.c_void_p(tris.data_ptr()), _stream_ptr(stream)))
+        else:
+            check(_lib.lib().voxb200_mesh_update_indexed(self._h, C.c_void_p(verts.data_ptr()), verts.numel() // 3, C.c_void_p(faces.data_ptr()), _stream_ptr(stream)))
+
+    def voxelize(self, table=None, accumulate=False, stream=None):
+        if table is None:
+            table = _new_table(self.grid, self.region, self.morton, "cuda")
+        check(_lib.lib().voxb200_mesh_voxelize(self._h, C.c_void_p(table.data_ptr()), ACCUMULATE if accumulate else 0, _stream_ptr(stream)))
+        return table
+
+    def info(self):
+        out = (C.c_uint64 * 8)()
+        check(_lib.lib().voxb200_mesh_info(self._h, out))
+        keys = ("tile_schedule", "tiles", "work_tiles", "instances", "side_triangles", "batches", "zero_quota", "zero_blocks")
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h and _lib is not None and C is not None:          # (module globals are gone at interpreter exit)
+            _lib.lib().voxb200_mesh_destroy(h)
+
+    __del__ = close

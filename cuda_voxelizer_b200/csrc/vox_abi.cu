@@ -214,6 +214,36 @@ int h2d(HostPath& hp, void* dst, const void* src, size_t bytes, cudaStream_t st)
 }  // namespace
 
 namespace voxb {
+int abi_fail(int code, const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+	return code;
+}
+int abi_fail_cuda(cudaError_t e, const char* what) { return fail_cuda(e, what); }
+int abi_current_ws(Workspace** out) { return current_ws(out); }
+int abi_resolve_region(const voxb200_grid* grid, const voxb200_region* region, bool morton, GridParams* g, size_t* region_words) {
+	return resolve_region(grid, region, morton, g, region_words);
+}
+int abi_init_workspace(Workspace& ws, int dev) {
+	cudaDeviceProp prop;
+	CU(cudaGetDeviceProperties(&prop, dev));
+	CU(cudaMalloc(&ws.counters, kNumCounters * sizeof(unsigned long long)));
+	CU(cudaMemset(ws.counters, 0, kNumCounters * sizeof(unsigned long long)));
+	ws.sm_count = prop.multiProcessorCount;
+	ws.device = dev;
+	return VOXB200_OK;
+}
+void abi_free_workspace(Workspace& ws) {
+	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch, ws.row_count, ws.row_marks};
+	for (void* p : dev_ptrs) if (p) cudaFree(p);
+	if (ws.prof_ev) {
+		for (int i = 0; i < kProfRing; i++) for (int k = 0; k < kProfEvents; k++) cudaEventDestroy(ws.prof_ev[i][k]);
+		delete[] ws.prof_ev;
+	}
+	ws = Workspace();
+}
 cudaError_t ensure_queue(Workspace& ws, size_t entries) {
 	if (entries <= ws.queue_cap) return cudaSuccess;
 	if (ws.queue) cudaFree(ws.queue);

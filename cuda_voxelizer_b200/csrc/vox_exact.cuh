@@ -151,19 +151,24 @@ __device__ __forceinline__ void edge_setup9(const float e_a[9], const float e_b[
 	d[8] = fadd(fadd(-fadd(m1[8], m2[8]), t1[8]), t2[8]);
 }
 
+// PLANE selects what is computed here: the normal and the plane offsets d1, d2 (:72, :83-87) — a prepared mesh stores them with
+// the triangle and passes PLANE = false — and, always, the nine edge functions (:91-125).
+template <bool PLANE = true>
 __device__ __forceinline__ void surf_setup_tests(const Tri& t, const GridParams& g, SurfSetup& s) {
 	// :68-70 edges
 	const float2 v0 = make_float2(t.v0x, t.v0y), v1 = make_float2(t.v1x, t.v1y), v2 = make_float2(t.v2x, t.v2y);
 	const float2 e0 = fsub2(v1, v0), e1 = fsub2(v2, v1), e2 = fsub2(v0, v2);
 	const float2 ez01 = fsub2(make_float2(t.v1z, t.v2z), make_float2(t.v0z, t.v1z));
 	const float e0x = e0.x, e0y = e0.y, e0z = ez01.x, e1x = e1.x, e1y = e1.y, e1z = ez01.y, e2x = e2.x, e2y = e2.y, e2z = fsub(t.v0z, t.v2z);
-	tri_normal(e0x, e0y, e0z, e1x, e1y, e1z, s.nx, s.ny, s.nz);
-	// :83-87 plane offsets
-	float cx = (s.nx > 0.0f) ? g.ux : 0.0f;
-	float cy = (s.ny > 0.0f) ? g.uy : 0.0f;
-	float cz = (s.nz > 0.0f) ? g.uz : 0.0f;
-	s.d1 = dot3(s.nx, s.ny, s.nz, fsub(cx, t.v0x), fsub(cy, t.v0y), fsub(cz, t.v0z));
-	s.d2 = dot3(s.nx, s.ny, s.nz, fsub(fsub(g.ux, cx), t.v0x), fsub(fsub(g.uy, cy), t.v0y), fsub(fsub(g.uz, cz), t.v0z));
+	if (PLANE) {
+		tri_normal(e0x, e0y, e0z, e1x, e1y, e1z, s.nx, s.ny, s.nz);
+		// :83-87 plane offsets
+		float cx = (s.nx > 0.0f) ? g.ux : 0.0f;
+		float cy = (s.ny > 0.0f) ? g.uy : 0.0f;
+		float cz = (s.nz > 0.0f) ? g.uz : 0.0f;
+		s.d1 = dot3(s.nx, s.ny, s.nz, fsub(cx, t.v0x), fsub(cy, t.v0y), fsub(cz, t.v0z));
+		s.d2 = dot3(s.nx, s.ny, s.nz, fsub(fsub(g.ux, cx), t.v0x), fsub(fsub(g.uy, cy), t.v0y), fsub(fsub(g.uz, cz), t.v0z));
+	}
 	// :91-101 XY (n_e = (-e.y, e.x), flipped if n.z < 0; offsets pair unit.x/unit.y); :103-113 YZ (n_e = (-e.z, e.y), flipped if
 	// n.x < 0; unit.y/unit.z); :115-125 ZX (n_e = (-e.x, e.z), flipped if n.y < 0).  The reference pairs unit.X with the first
 	// ZX component (the coefficient of p.z) and unit.Z with the second (§A-13): kept verbatim.

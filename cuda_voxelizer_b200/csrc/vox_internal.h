@@ -95,6 +95,71 @@ cudaError_t launch_route_count(const GridParams& g, bool solid, const int (*lo)[
                                unsigned int* d_masks, unsigned long long* d_counts, cudaStream_t st);
 cudaError_t launch_route_scatter(unsigned long long n_tris, int n_regions, const float* d_soup, const unsigned int* d_masks, float* d_out,
                                  unsigned long long* d_cursors, cudaStream_t st);
+// ---- tile-owner surface path of a prepared mesh (tiles.cu) ------------------------------------------------
+// A tile is Tx x kTileY x kTileZ voxels with Tx = min(G, 1024): its row segments are whole 128-byte lines (or whole rows), so the
+// owning block's clears and atomics never share an L2 line with another block.
+#ifndef VOXB_TILE_Y
+#define VOXB_TILE_Y 16
+#endif
+#ifndef VOXB_TILE_Z
+#define VOXB_TILE_Z 16
+#endif
+constexpr int kTileY = VOXB_TILE_Y, kTileZ = VOXB_TILE_Z;
+constexpr int kTileXMax = 1024;
+constexpr int kZeroBlockChunks = 256;                      // 512-byte chunks per zero-only block of the tile kernel (128 KB)
+struct TileGeom {
+	int ntx, nty, ntz;              // tiles per axis inside the region
+	int tx_shift;                   // log2 of the tile's x-extent in voxels (8..10)
+	int chunk_shift;                // log2 of the 512-byte zero-fill chunks per tile
+	int G;
+	int tz0;                        // first tile layer of the region (region z0 / kTileZ)
+	unsigned int n_tiles;
+};
+enum PlanTotal {                    // device-side totals of the planning pass (u64 each)
+	kPlanInstances = 0,             // (triangle, tile) records
+	kPlanEmpty = 1, kPlanWork = 2,  // empty / non-empty tiles
+	kPlanBatches = 3,               // 32-triangle batches over all non-empty tiles
+	kPlanBigDirect = 4,             // triangles whose bbox exceeds 4x4x4 voxels
+	kPlanHeavyInstances = 5,        // instances that fell into over-full tiles (they take the side path)
+	kPlanSideFill = 6,              // triangles written to the side soup
+	kPlanWide = 7,                  // small triangles that need the 64-candidate evaluation
+	kPlanTotals = 8
+};
+struct TilePlan {
+	TileGeom geom;
+	const float* soup;              // 64-byte records (tiles.cu), one per (triangle, tile); the run of tile t starts at record off[t]
+	const unsigned int* cnt;        // triangles per tile
+	const unsigned int* off;
+	const unsigned int* order;      // non-empty tiles, heaviest first (n_work)
+	const unsigned int* bprefix;    // batches before work item w (n_work + 1)
+	const unsigned int* empty;      // empty tiles in table order (n_empty): the table word, relative to the region, of each one's first voxel
+	unsigned int n_work, n_empty;
+	unsigned int zero_chunks;       // 16 * n_empty chunks of 512 bytes
+	unsigned int zero_quota;        // chunks every 32-triangle batch clears
+	unsigned int zero_rest_first, n_zero_blocks;      // chunks from here on are cleared by zero-only blocks
+	bool wide;                      // some binned triangle needs the <=4x4x4 evaluation
+};
+cudaError_t launch_tile_count(const GridParams& g, const TileGeom& tg, const float* d_soup, const float* d_verts, const int* d_faces,
+                              unsigned int* d_keys, unsigned int* d_cnt, unsigned long long* d_totals, cudaStream_t st);
+cudaError_t launch_tile_plan(const TileGeom& tg, unsigned int cap, const unsigned int* d_cnt, unsigned int* d_off, unsigned int* d_order,
+                             unsigned int* d_bprefix, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st);
+cudaError_t launch_tile_scatter(const GridParams& g, const TileGeom& tg, unsigned int cap, const float* d_soup, const float* d_verts,
+                                const int* d_faces, const unsigned int* d_keys, const unsigned int* d_cnt, const unsigned int* d_off,
+                                unsigned int* d_fill, void* d_records, float* d_side, unsigned long long* d_totals, cudaStream_t st);
+cudaError_t launch_surface_tiles(const GridParams& g, const TilePlan& p, unsigned int* d_table, bool accumulate, cudaStream_t st);
+
+// ---- shared by the ABI translation units (defined in vox_abi.cu) ---------------------------------------------
+int abi_fail(int code, const char* fmt, ...);
+int abi_fail_cuda(cudaError_t e, const char* what);
+int abi_current_ws(Workspace** out);                 // the calling thread's current device's library workspace
+int abi_init_workspace(Workspace& ws, int dev);      // a private workspace (prepared meshes own one each)
+void abi_free_workspace(Workspace& ws);
+}  // namespace voxb
+struct voxb200_grid;
+struct voxb200_region;
+namespace voxb {
+int abi_resolve_region(const ::voxb200_grid* grid, const ::voxb200_region* region, bool morton, GridParams* g, size_t* region_words);
+
 // Table consumer: set voxels -> ascending voxel indices
 size_t extract_blocks(size_t n_words);
 cudaError_t launch_extract_count(const unsigned int* d_table, size_t n_words, unsigned int* d_counts, unsigned long long* d_offsets, cudaStream_t st);

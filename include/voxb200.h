@@ -25,6 +25,7 @@
  *   voxb200_solid ........................ voxelize_solid()               src/voxelize_solid.cu:147-193 (kernel :73-145)
  *   voxb200_morton_encode ................ mortonEncode_LUT()             src/voxelize.cuh:20-34
  *   voxb200_voxelize_host ................ main.cpp:203-222 (upload + voxelize + table read-back by the writers)
+ *   voxb200_mesh_* ....................... (new) prepared mesh for repeated voxelization (README.md:74 "per-frame")
  *   bit-table layout ..................... setBit / checkVoxel            src/voxelize.cu:50-55, src/util.h:25-38
  */
 #ifndef VOXB200_H
@@ -185,6 +186,37 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
  */
 int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]);
+
+/* ---- prepared meshes: the resident / per-frame interface ------------------------------------------------ */
+/*
+ * The reference voxelizes a mesh once per process (main.cpp:203-222) although it pitches per-frame use (README.md:74).
+ * A voxb200_mesh is a mesh prepared for ONE grid (and region): it owns a re-ordered copy of the triangles, the plan of
+ * the tile-owner surface schedule and a private workspace, so
+ *   - voxb200_mesh_voxelize only enqueues kernels on `stream` (no allocation, no synchronisation, capturable into a
+ *     CUDA graph) and is RE-ENTRANT: different meshes may voxelize concurrently on different streams of a device;
+ *   - a surface voxelization in linear order on a grid whose size is a multiple of 256 (<= 4096) writes every table
+ *     byte exactly once: tiles of 256x16x16 voxels are assembled in shared memory by the one thread block that owns
+ *     them, the empty tiles are cleared on the side — no zero-fill pass, no global atomics except for the triangles
+ *     larger than 4x4x4 voxels, which take the row-solver path afterwards.  Every other configuration (solid, morton
+ *     order, other grid sizes) runs the one-shot kernels on the handle's own data.
+ * The table is bit-identical to voxb200_surface / voxb200_solid on the same triangles.
+ * flags of _create: VOXB200_SOLID, VOXB200_MORTON.  flags of _voxelize: VOXB200_ACCUMULATE.
+ * _create / _update synchronise `stream` (they size buffers from device-side counts); _update re-prepares the mesh for new
+ * vertex positions (same triangle count) reusing the handle's buffers.  The triangle arrays are not referenced after
+ * the call returns.  voxb200_mesh_info: [0] 1 = tile schedule, [1] tiles, [2] non-empty tiles, [3] binned triangle
+ * instances, [4] triangles on the row-solver side path, [5] 32-triangle batches, [6] zero-fill chunks per batch,
+ * [7] zero-only blocks.
+ */
+typedef struct voxb200_mesh voxb200_mesh;
+int voxb200_mesh_create(const voxb200_grid* grid, const float* d_tris9, unsigned int flags, const voxb200_region* region,
+                        voxb200_mesh** out, void* stream);
+int voxb200_mesh_create_indexed(const voxb200_grid* grid, const float* d_verts, size_t n_verts, const int32_t* d_faces, unsigned int flags,
+                                const voxb200_region* region, voxb200_mesh** out, void* stream);
+int voxb200_mesh_update(voxb200_mesh* mesh, const float* d_tris9, void* stream);
+int voxb200_mesh_update_indexed(voxb200_mesh* mesh, const float* d_verts, size_t n_verts, const int32_t* d_faces, void* stream);
+int voxb200_mesh_voxelize(voxb200_mesh* mesh, unsigned int* d_table, unsigned int flags, void* stream);
+int voxb200_mesh_info(const voxb200_mesh* mesh, uint64_t out[8]);
+int voxb200_mesh_destroy(voxb200_mesh* mesh);
 
 /*
  * Table consumer (replaces the G^3 host checkVoxel() loops of the writers, src/util_io.cpp:92-285): compacts the set
