@@ -35,7 +35,8 @@ struct voxb200_mesh {
 	float* binned = nullptr; size_t binned_cap = 0;        // records (in floats)
 	float* side = nullptr; size_t side_cap = 0;            // triangles
 	size_t n_side = 0;
-	unsigned int *cnt = nullptr, *off = nullptr, *order = nullptr, *bprefix = nullptr, *empty = nullptr, *fill = nullptr;
+	unsigned int *cnt = nullptr, *off = nullptr, *order = nullptr, *empty = nullptr, *fill = nullptr;
+	uint4* work = nullptr;
 	size_t tiles_cap = 0;
 	unsigned int* keys = nullptr; size_t keys_cap = 0;
 	unsigned long long* totals = nullptr;
@@ -111,9 +112,12 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 	tg.n_tiles = (unsigned int)tg.ntx * (unsigned int)tg.nty * (unsigned int)tg.ntz;
 	const size_t nt = tg.n_tiles;
 	if (nt + 1 > m.tiles_cap || !m.cnt) {
-		for (unsigned int** p : {&m.cnt, &m.off, &m.order, &m.bprefix, &m.empty, &m.fill}) { if (*p) cudaFree(*p); *p = nullptr; }
+		for (unsigned int** p : {&m.cnt, &m.off, &m.order, &m.empty, &m.fill}) { if (*p) cudaFree(*p); *p = nullptr; }
+		if (m.work) cudaFree(m.work);
+		m.work = nullptr;
 		m.tiles_cap = 0;
-		for (unsigned int** p : {&m.cnt, &m.off, &m.order, &m.bprefix, &m.empty, &m.fill}) CU(cudaMalloc(p, (nt + 1) * sizeof(unsigned int)));
+		for (unsigned int** p : {&m.cnt, &m.off, &m.order, &m.empty, &m.fill}) CU(cudaMalloc(p, (nt + 1) * sizeof(unsigned int)));
+		CU(cudaMalloc(&m.work, (nt + 1) * sizeof(uint4)));
 		m.tiles_cap = nt + 1;
 	}
 	if (!m.totals) CU(cudaMalloc(&m.totals, kPlanTotals * sizeof(unsigned long long)));
@@ -122,7 +126,7 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 	// a tile whose run would keep one CTA busy for a large part of the whole kernel is not binned: its triangles take the side path
 	const unsigned int cap = (unsigned int)(n / 256 > 8192 ? n / 256 : 8192);
 	cudaError_t e = launch_tile_count(g, tg, d_soup, d_verts, d_faces, m.keys, m.cnt, m.totals, st);
-	if (e == cudaSuccess) e = launch_tile_plan(tg, cap, m.cnt, m.off, m.order, m.bprefix, m.empty, m.totals, st);
+	if (e == cudaSuccess) e = launch_tile_plan(tg, cap, m.cnt, m.off, m.order, m.work, m.empty, m.totals, st);
 	if (e == cudaSuccess) e = cudaMemcpyAsync(m.host_totals, m.totals, sizeof(m.host_totals), cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) return abi_fail_cuda(e, "voxb200_mesh prepare (count / plan)");
@@ -139,7 +143,7 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 	m.n_side = (size_t)m.host_totals[kPlanSideFill];
 	TilePlan& p = m.plan;
 	p.geom = tg;
-	p.soup = m.binned; p.cnt = m.cnt; p.off = m.off; p.order = m.order; p.bprefix = m.bprefix; p.empty = m.empty;
+	p.soup = m.binned; p.cnt = m.cnt; p.off = m.off; p.order = m.order; p.work = m.work; p.empty = m.empty;
 	p.n_work = (unsigned int)m.host_totals[kPlanWork];
 	p.wide = m.host_totals[kPlanWide] != 0;
 	p.n_empty = (unsigned int)m.host_totals[kPlanEmpty];
@@ -178,7 +182,7 @@ int create_common(const voxb200_grid* grid, unsigned int flags, const voxb200_re
 }
 
 void destroy(voxb200_mesh* m) {
-	for (void* p : {(void*)m->binned, (void*)m->side, (void*)m->cnt, (void*)m->off, (void*)m->order, (void*)m->bprefix, (void*)m->empty,
+	for (void* p : {(void*)m->binned, (void*)m->side, (void*)m->cnt, (void*)m->off, (void*)m->order, (void*)m->work, (void*)m->empty,
 	                (void*)m->fill, (void*)m->keys, (void*)m->totals, (void*)m->soup, (void*)m->sort_keys, (void*)m->sort_hist})
 		if (p) cudaFree(p);
 	abi_free_workspace(m->ws);

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(kPrepBlock) tile_count_kernel(const GridParams
 // One CTA of 1024 threads plans the whole grid of tiles (n_tiles <= 2^20): see the header comment.
 __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, const unsigned int cap, const unsigned int* __restrict__ cnt,
                                                          unsigned int* __restrict__ off, unsigned int* __restrict__ order,
-                                                         unsigned int* __restrict__ bprefix, unsigned int* __restrict__ empty,
+                                                         uint4* __restrict__ work, unsigned int* __restrict__ empty,
                                                          unsigned long long* __restrict__ totals) {
 	__shared__ unsigned long long s_inst[1024];
 	__shared__ unsigned int s_empty[1024], s_work[1024], s_batches[1024];
@@ -198,12 +198,20 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, cons
 	if (threadIdx.x == 0) {
 		unsigned int run = 0u;
 		for (int k = 0; k < 1024; k++) { const unsigned int v = s_batches[k]; s_batches[k] = run; run += v; }
-		bprefix[nw] = run;
 		totals[kPlanBatches] = run;
 	}
 	__syncthreads();
 	unsigned int run = s_batches[threadIdx.x];
-	for (unsigned int w = wa; w < wb; w++) { bprefix[w] = run; run += (cnt[order[w]] + 31u) >> 5; }
+	for (unsigned int w = wa; w < wb; w++) {
+		// everything a tile block needs, in one 16-byte load: {table word of the tile's first voxel, records, first record, batches before it}
+		const unsigned int t = order[w], c = cnt[t];
+		const unsigned int tx = t % (unsigned int)tg.ntx, r = t / (unsigned int)tg.ntx;
+		const unsigned int ty = r % (unsigned int)tg.nty, tzl = r / (unsigned int)tg.nty;
+		const unsigned long long G = (unsigned long long)tg.G;
+		const unsigned int word = (unsigned int)((((unsigned long long)tzl * kTileZ * G + (unsigned long long)ty * kTileY) * G + ((unsigned long long)tx << tg.tx_shift)) >> 5);
+		work[w] = make_uint4(word, c, off[t], run);
+		run += (c + 31u) >> 5;
+	}
 }
 
 // The 64-byte record of one (triangle, tile) pair:
@@ -290,8 +298,8 @@ cudaError_t launch_tile_count(const GridParams& g, const TileGeom& tg, const flo
 }
 
 cudaError_t launch_tile_plan(const TileGeom& tg, unsigned int cap, const unsigned int* d_cnt, unsigned int* d_off, unsigned int* d_order,
-                             unsigned int* d_bprefix, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st) {
-	tile_plan_kernel<<<1, 1024, 0, st>>>(tg, cap, d_cnt, d_off, d_order, d_bprefix, d_empty, d_totals);
+                             void* d_work, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st) {
+	tile_plan_kernel<<<1, 1024, 0, st>>>(tg, cap, d_cnt, d_off, d_order, reinterpret_cast<uint4*>(d_work), d_empty, d_totals);
 	g_launch_count++;
 	return cudaGetLastError();
 }
@@ -312,22 +320,18 @@ cudaError_t launch_tile_scatter(const GridParams& g, const TileGeom& tg, unsigne
 // ------------------------------------------------------------------------------------------------
 // voxelize
 // ------------------------------------------------------------------------------------------------
-// Tile t -> its first voxel
-__device__ __forceinline__ void tile_origin(const TilePlan& p, unsigned int t, int& x0t, int& y0t, int& z0t) {
-	const unsigned int tx = t % (unsigned int)p.geom.ntx, r = t / (unsigned int)p.geom.ntx;
-	const unsigned int ty = r % (unsigned int)p.geom.nty, tzl = r / (unsigned int)p.geom.nty;
-	x0t = (int)(tx << p.geom.tx_shift); y0t = (int)ty * kTileY; z0t = (int)(tzl + (unsigned int)p.geom.tz0) * kTileZ;
-}
 // Chunk c (512 bytes) of the empty space — the empty tiles back to back; p.empty holds the table word of each one's first voxel.
 // A chunk is 4096 >> tx_shift consecutive row segments (y fastest), Tx / 128 lanes of 16 bytes per segment.
-__device__ __forceinline__ void zero_chunk(const GridParams& g, const TilePlan& p, unsigned int* __restrict__ table, unsigned int c, int lane) {
-	const unsigned int base = __ldg(p.empty + (c >> p.geom.chunk_shift));
+__device__ __forceinline__ void zero_chunk_at(const GridParams& g, const TilePlan& p, unsigned int* __restrict__ table, unsigned int base, unsigned int c, int lane) {
 	const unsigned int sub = c & ((1u << p.geom.chunk_shift) - 1u);
 	const int lanes_shift = p.geom.tx_shift - 7;
 	const unsigned int row = (sub << (5 - lanes_shift)) + ((unsigned int)lane >> lanes_shift);
 	const unsigned int Gw = (unsigned int)g.G >> 5;
 	const unsigned int word = base + ((row / (unsigned int)kTileY) * (unsigned int)g.G + (row % (unsigned int)kTileY)) * Gw + 4u * ((unsigned int)lane & ((1u << lanes_shift) - 1u));
 	*reinterpret_cast<uint4*>(table + word) = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void zero_chunk(const GridParams& g, const TilePlan& p, unsigned int* __restrict__ table, unsigned int c, int lane) {
+	zero_chunk_at(g, p, table, __ldg(p.empty + (c >> p.geom.chunk_shift)), c, lane);
 }
 
 #ifndef VOXB_RED_BLOCK
@@ -363,39 +367,40 @@ __global__ void __launch_bounds__(kRedBlock, WIDE ? 4 : VOXB_RED_MINB) surface_t
 		for (unsigned int c = c0 + warp; c < c1; c += kRedBlock / 32) zero_chunk(g, p, table, c, lane);
 		return;
 	}
-	const unsigned int w = blockIdx.x - p.n_zero_blocks;
-	const unsigned int t = __ldg(p.order + w);
-	const unsigned int cnt = __ldg(p.cnt + t), off = __ldg(p.off + t);
-	const unsigned int nb = (cnt + 31u) >> 5;
-	const unsigned int bp = __ldg(p.bprefix + w);
-	const uint4* recs = reinterpret_cast<const uint4*>(p.soup) + 4ull * off;
+	const uint4 wk = __ldg(p.work + (blockIdx.x - p.n_zero_blocks));       // {tile's first table word, records, first record, batches before}
+	const unsigned int cnt = wk.y, nb = (wk.y + 31u) >> 5, bp = wk.w;
+	const uint4* recs = reinterpret_cast<const uint4*>(p.soup) + 4ull * wk.z;
 	uint4* my_stage = stage + warp * 2 * kBatchVec;
 	if ((unsigned int)warp < nb) fetch_batch(recs + (size_t)warp * kBatchVec, my_stage, lane);        // in flight during the clear
 	if (!ACC) {
 		// clear the tile: a thread's 16-byte pieces are a whole number of z-layers apart, so one address and a constant stride
-		int x0t, y0t, z0t;
-		tile_origin(p, t, x0t, y0t, z0t);
 		const int lanes_shift = p.geom.tx_shift - 7;                                       // lanes per row segment = Tx / 128
 		const unsigned int row = threadIdx.x >> lanes_shift;
-		const unsigned long long G = (unsigned long long)g.G;
-		const unsigned long long y = (unsigned long long)y0t + (row % (unsigned int)kTileY), z = (unsigned long long)z0t + (row / (unsigned int)kTileY);
-		uint4* dst = reinterpret_cast<uint4*>(table + ((((z * G + y) * G + (unsigned long long)x0t) >> 5) - g.word_base)) + (threadIdx.x & ((1u << lanes_shift) - 1u));
+		const unsigned int Gw = (unsigned int)g.G >> 5;
+		uint4* dst = reinterpret_cast<uint4*>(table + (wk.x + ((row / (unsigned int)kTileY) * (unsigned int)g.G + (row % (unsigned int)kTileY)) * Gw)) +
+		             (threadIdx.x & ((1u << lanes_shift) - 1u));
 		const int layers_per_step = (kRedBlock >> lanes_shift) / kTileY;                  // the block's threads cover this many z-layers per step
-		const size_t stride = (size_t)layers_per_step * (size_t)(G * G / 128ull);         // in 16-byte units
+		const size_t stride = (size_t)layers_per_step * ((size_t)g.G * (size_t)g.G / 128u);      // in 16-byte units
 		for (int k = 0; k < kTileZ / layers_per_step; k++) dst[(size_t)k * stride] = make_uint4(0u, 0u, 0u, 0u);
-		__threadfence();             // the cleared lines are visible device-wide before any thread of the block ORs into them
-		__syncthreads();
 	}
+	// The clears must be ordered before every red.or of the block into the tile.  Both come from threads of THIS block and no other
+	// block touches the tile during the kernel, so a block barrier is all the ordering needed (accesses made before bar.sync are
+	// visible to every thread of the block after it, and an atomic acts on the visible value; a device-scope fence would only add a
+	// store drain: it cost 10 % of the kernel when it was here).  The barrier sits in front of the first SCATTER, not the first
+	// batch, so nobody waits for the clears before there is something to write.
+	bool unfenced = !ACC;
 	int buf = 0;
 #pragma unroll 1
 	for (unsigned int b = warp; b < nb; b += kRedBlock / 32) {
-		// the next batch's records, and this batch's share of the empty space, while this batch's records arrive
+		// this batch's share of the empty space: the tile address now, the stores after the arithmetic
+		unsigned int c0 = 0u, c1 = 0u, zbase = 0u;
+		if (!ACC) {
+			c0 = min(p.zero_chunks, (bp + b) * p.zero_quota); c1 = min(p.zero_chunks, c0 + p.zero_quota);
+			if (c0 < c1) zbase = __ldg(p.empty + (c0 >> p.geom.chunk_shift));
+		}
+		// the next batch's records while this batch's arrive
 		const unsigned int bn = b + kRedBlock / 32;
 		if (bn < nb) fetch_batch(recs + (size_t)bn * kBatchVec, my_stage + (buf ^ 1) * kBatchVec, lane);
-		if (!ACC) {
-			const unsigned int c0 = min(p.zero_chunks, (bp + b) * p.zero_quota), c1 = min(p.zero_chunks, c0 + p.zero_quota);
-			for (unsigned int c = c0; c < c1; c++) zero_chunk(g, p, table, c, lane);
-		}
 		if (bn < nb) asm volatile("cp.async.wait_group 1;" ::: "memory");
 		else asm volatile("cp.async.wait_group 0;" ::: "memory");
 		__syncwarp();
@@ -417,15 +422,27 @@ __global__ void __launch_bounds__(kRedBlock, WIDE ? 4 : VOXB_RED_MINB) surface_t
 		s.x1 = s.x0 + ex; s.y1 = s.y0 + ey; s.z1 = s.z0 + ez;
 		if (live) surf_setup_tests<false>(tr, g, s);
 		const bool wide = WIDE && __any_sync(0xffffffffu, live && (ex == 3 || ey == 3 || ez == 3));
+		unsigned long long hit4 = 0ull;
+		unsigned int hit = 0u;
+		if (wide) hit4 = live ? surf_micro4(s, g) : 0ull;
+		else hit = live ? surf_micro3(s, g) : 0u;
+		if (unfenced) {
+			asm volatile("bar.sync 1, %0;" ::"n"(kRedBlock) : "memory");
+			unfenced = false;
+		}
 		if (wide) {
-			const unsigned long long hit = live ? surf_micro4(s, g) : 0ull;
-			if (hit) scatter_hits4<false>(hit, s.x0, s.y0, s.z0, g, table);
+			if (hit4) scatter_hits4<false>(hit4, s.x0, s.y0, s.z0, g, table);
 		} else {
-			const unsigned int hit = live ? surf_micro3(s, g) : 0u;
 			if (!live) { s.x0 = g.rx0; s.y0 = g.ry0; s.z0 = g.rz0; }
 			scatter_hits3<false>(hit, s.x0, s.y0, s.z0, g, table);      // converged: every write is predicated on its own bits
 		}
+		// (the empty tiles are nobody's: no ordering needed)
+		for (unsigned int c = c0; c < c1; c++) {
+			const unsigned int base = (c >> p.geom.chunk_shift) == (c0 >> p.geom.chunk_shift) ? zbase : __ldg(p.empty + (c >> p.geom.chunk_shift));
+			zero_chunk_at(g, p, table, base, c, lane);
+		}
 	}
+	if (unfenced) asm volatile("bar.sync 1, %0;" ::"n"(kRedBlock) : "memory");          // a warp without batches still owes its arrival
 }
 
 template <bool ACC, bool WIDE>

@@ -131,7 +131,7 @@ struct TilePlan {
 	const unsigned int* cnt;        // triangles per tile
 	const unsigned int* off;
 	const unsigned int* order;      // non-empty tiles, heaviest first (n_work)
-	const unsigned int* bprefix;    // batches before work item w (n_work + 1)
+	const uint4* work;              // per non-empty tile, heaviest first (n_work): {table word of its first voxel, records, first record, batches before it}
 	const unsigned int* empty;      // empty tiles in table order (n_empty): the table word, relative to the region, of each one's first voxel
 	unsigned int n_work, n_empty;
 	unsigned int zero_chunks;       // 16 * n_empty chunks of 512 bytes
@@ -142,7 +142,7 @@ struct TilePlan {
 cudaError_t launch_tile_count(const GridParams& g, const TileGeom& tg, const float* d_soup, const float* d_verts, const int* d_faces,
                               unsigned int* d_keys, unsigned int* d_cnt, unsigned long long* d_totals, cudaStream_t st);
 cudaError_t launch_tile_plan(const TileGeom& tg, unsigned int cap, const unsigned int* d_cnt, unsigned int* d_off, unsigned int* d_order,
-                             unsigned int* d_bprefix, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st);
+                             void* d_work, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st);
 cudaError_t launch_tile_scatter(const GridParams& g, const TileGeom& tg, unsigned int cap, const float* d_soup, const float* d_verts,
                                 const int* d_faces, const unsigned int* d_keys, const unsigned int* d_cnt, const unsigned int* d_off,
                                 unsigned int* d_fill, void* d_records, float* d_side, unsigned long long* d_totals, cudaStream_t st);
