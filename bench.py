@@ -11,9 +11,14 @@ GPUs the SAME mesh is voxelized once: rank r owns z-slab r of the bit table (dis
 reduction, no data-path collective), every rank reads the replicated triangle soup.  Total work is
 fixed, so scaling is "strong".
 
-A step = one full voxelization: zero-fill of the rank's slab + per-triangle kernel + cooperative kernel.
+A step = one full voxelization of the rank's slab.  Surface workloads run through the prepared-mesh interface
+(voxb200_mesh_*, the resident / per-frame API): the TIMED REGION is one voxb200_mesh_update — the re-ordering of the
+caller's triangle soup into the tile records, from the caller's order, buffers reused — followed by K voxb200_mesh_voxelize
+calls (one captured CUDA graph replayed K times), so the preparation is inside the headline number, amortised over the K
+steps the command line asks for.  The line also carries "resident" (the K steps alone), "prepare_ms", and "one_shot"
+(voxb200_surface on the caller's order: what a single voxelization without preparation costs).
   value : Mtri/s with triangles resident in HBM (device time, CUDA events, max over ranks)
-  e2e   : Mtri/s through voxb200_voxelize_host_indexed — pinned host mesh -> H2D -> expand -> voxelize -> D2H of the slab
+  e2e   : Mtri/s through voxb200_voxelize_host_indexed — pinned host mesh -> H2D -> tile records -> voxelize -> D2H of the slab
 """
 import argparse
 import json
@@ -134,6 +139,11 @@ def pick_cpu_threads(verts, faces, G, solid):
     return (1 if t_one <= t_all else max_thr), max_thr, {"1": round(t_one, 1), str(max_thr): round(t_all, 1)}, kind, n_cal
 
 
+def bench_config(w, n_tris):
+    """The `config` object both arms print (identical, so the driver can tell they ran the same work)."""
+    return {"workload": w["desc"], "gridsize": w["G"], "triangles": int(n_tris), "mode": "solid" if w["solid"] else "surface"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -142,9 +152,9 @@ def run_reference(args):
     w = WORKLOADS[wname]
     verts, faces = load_mesh(wname)
     threads, max_thr, cal, kind, n_cal = pick_cpu_threads(verts, faces, w["G"], w["solid"])
-    # bounded sample per step: aim at ~2 s of CPU work per step
-    per_tri_ms = cal[str(threads)] / n_cal
-    n_sample = int(min(len(faces), max(1000, 2000.0 / max(per_tri_ms, 1e-9))))
+    n_sample = len(faces)              # the whole mesh every step: the same work as the GPU arm
+    if args.reference_sample:
+        n_sample = min(len(faces), args.reference_sample)
     for _ in range(args.warmup):
         cpu_reference_run(verts, faces, w["G"], w["solid"], n_sample, threads)
     total_ms = 0.0
@@ -153,14 +163,16 @@ def run_reference(args):
         total_ms += ms
     ms_per_step = total_ms / args.steps
     value = n_sample / ms_per_step / 1e3
-    sample = ("first %d of %d triangles of the workload per step, whole %d^3 grid; %d thread(s) chosen by calibration %s ms on %d tris "
+    sample = ("all %d triangles of the workload per step, whole %d^3 grid; %d thread(s) chosen by calibration %s ms on %d tris "
               "(host has %d hardware threads; the reference's global omp critical makes more threads slower)"
-              % (n_sample, len(faces), w["G"], threads, cal, n_cal, max_thr))
+              % (n_sample, w["G"], threads, cal, n_cal, max_thr))
+    if n_sample != len(faces):
+        sample = "first %d of %d triangles (--reference-sample); " % (n_sample, len(faces)) + sample
     line = {
         "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": "Mtri/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 3), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "gridsize": w["G"], "triangles": int(len(faces)), "mode": "solid" if w["solid"] else "surface"},
+        "config": bench_config(w, len(faces)),
         "cpu_baseline": {"value": round(value, 4), "unit": "Mtri/s", "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 4), "unit": "Mtri/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -217,36 +229,47 @@ def run_ours(args):
         del d_all
         torch.cuda.empty_cache()
 
-    def step():
+    def one_shot_step():
         fn(step_grid, d_tris, table=table, region=region_arg)          # on torch's current stream (the capture stream during capture)
 
-    # ---- the caller's triangle order first (a few direct steps), then the upload path's z-layer order ----------
-    # voxb200_sort_triangles is an upload-path option for meshes voxelized more than once: same table bits (OR does not
-    # depend on the order), but the atomics sweep the table front to back and stay in L2.  It is done ONCE, outside the
-    # timed region (like the routing at N > 1), its cost is reported, and e2e (one-shot from host memory) does not use it.
-    unsorted, sort_ms = None, None
-    if not solid and not args.no_sort:
-        for _ in range(max(args.warmup, 3)):
-            step()
+    def timed(run, n):
         barrier()
-        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n_u = max(1, min(args.steps, 10))
-        u0.record(stream)
-        for _ in range(n_u):
-            step()
-        u1.record(stream)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(n):
+            run()
+        b.record(stream)
         barrier()
-        tu = torch.tensor([u0.elapsed_time(u1) / n_u], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([a.elapsed_time(b) / n], dtype=torch.float64, device="cuda")
         if world > 1:
-            dist.all_reduce(tu, op=dist.ReduceOp.MAX)
-        unsorted = {"ms_per_step": round(float(tu.item()), 4), "value": round(n_tris / float(tu.item()) / 1e3, 2), "unit": "Mtri/s",
-                    "note": "the caller's triangle order, direct launches, %d steps" % n_u}
-        vb.sort_triangles(step_grid, d_tris).close()                    # warm-up (allocations)
-        torch.cuda.synchronize()
-        t_sort = time.perf_counter()
-        d_sorted = vb.sort_triangles(step_grid, d_tris)                 # synchronous
-        sort_ms = (time.perf_counter() - t_sort) * 1e3
-        d_tris = d_sorted
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    # ---- what one voxelization costs WITHOUT preparation: voxb200_surface / voxb200_solid on the soup in the caller's order ----
+    for _ in range(max(args.warmup, 3)):
+        one_shot_step()
+    n_u = max(1, min(args.steps, 10))
+    t_one = timed(one_shot_step, n_u)
+    one_shot = {"ms_per_step": round(t_one, 4), "value": round(n_tris / t_one / 1e3, 2), "unit": "Mtri/s",
+                "note": "voxb200_%s on the device soup in the caller's triangle order, direct launches, %d steps" % ("solid" if solid else "surface", n_u)}
+
+    # ---- the prepared mesh (surface workloads): created once (allocations), re-prepared inside the timed region ----
+    use_mesh = not solid and not args.one_shot
+    mesh, mesh_info, prepare_ms = None, None, None
+    if use_mesh:
+        mesh = vb.Mesh(step_grid, tris=d_tris, region=region_arg)
+        mesh_info = mesh.info()
+
+        def step():
+            mesh.voxelize(table=table)
+
+        def prepare():
+            mesh.update(tris=d_tris)
+        for _ in range(2):
+            prepare()
+        prepare_ms = timed(prepare, 3)
+    else:
+        step, prepare = one_shot_step, None
 
     # ---- device-resident timing -----------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -256,7 +279,7 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    # The timed loop replays ONE captured CUDA graph of the step (the library only enqueues on the caller's stream, so a whole
+    # The K steps replay ONE captured CUDA graph of the step (the library only enqueues on the caller's stream, so a whole
     # voxelization is capturable): the kernels are the same, the host-side launch gaps between them are not paid K times.
     graph = None
     if not args.no_graph:
@@ -270,17 +293,23 @@ def run_ours(args):
         except Exception as exc:      # capture not possible: time the direct calls
             sys.stderr.write("bench: CUDA graph capture failed (%s); timing direct launches\n" % exc)
             graph = None
+
+    def run_steps():
+        for _ in range(args.steps):
+            if graph is not None:
+                graph.replay()
+            else:
+                step()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
-        if graph is not None:
-            graph.replay()
-        else:
-            step()
+    if prepare is not None:
+        prepare()                     # the caller's order -> tile records: inside the timed region, amortised over the K steps
+    run_steps()
     ev1.record(stream)
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
+    resident_ms = timed(run_steps, 1) / args.steps        # the K steps alone
     # per-kernel times and the launch count come from a separate, untimed pass of direct calls with the library's event ring on
     vb.set_profiling(True)
     launches0 = vb.launch_count()
@@ -291,7 +320,7 @@ def run_ours(args):
     launches = (vb.launch_count() - launches0) // n_prof * args.steps
     phases = np.array([vb.phase_ms(i) for i in range(n_prof)], np.float64).mean(axis=0)
     vb.set_profiling(False)
-    counters = vb.last_counters()
+    counters = mesh.counters() if mesh is not None else vb.last_counters()
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -317,7 +346,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_wall_ms = (time.perf_counter() - t0) * 1e3
         e2e_h2d_bytes = int(pinned_verts.numel() * 4 + pinned_faces.numel() * 4)
-    e2e_api = "voxb200_voxelize_host_indexed (pinned host vertices+faces -> H2D -> expand -> voxelize -> D2H table slab)"
+    e2e_api = "voxb200_voxelize_host_indexed (pinned host vertices+faces -> H2D -> tile records / expand -> voxelize -> D2H table slab)"
     if world > 1:
         # N > 1: the upload is sharded too.  Rank r holds 1/N of the soup in pinned memory, uploads only that, routes it
         # on the GPU to the N slabs, swaps triangles in one all-to-all over NVLink, voxelizes its slab, reads it back.
@@ -386,34 +415,41 @@ def run_ours(args):
 
     # ---- roofline of the dominant kernel ----------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    tri_bytes = 36 * n_tris
     slab_bytes = region_bytes
     tri_bytes = 36 * (routed if world > 1 else n_tris)
-    names = ["zero_kernel", "surface_tri_kernel" if not solid else "solid_tri_kernel",
-             "surface_coop_kernel" if not solid else "solid_coop_kernel", "solid_scan_kernel"]
-    alg_bytes = [slab_bytes, tri_bytes, 0, 2 * slab_bytes if solid else 0]
-    if solid and counters.get("solid_row_lists"):
-        # row-list schedule: no zero-fill (phase 0 is the 64-byte counter reset), the fill writes every table byte once
-        names[0], names[3] = "counter_reset", "solid_fill_kernel"
-        alg_bytes[0], alg_bytes[3] = 0, slab_bytes
+    if mesh is not None and mesh_info["tile_schedule"]:
+        # phases of voxb200_mesh_voxelize: [-, tile kernel (clears the slab AND voxelizes the small triangles), side path, -]
+        names = ["-", "surface_tile_kernel", "side path: surface_tri_kernel + surface_coop_kernel (big triangles)", "-"]
+        alg_bytes = [0, tri_bytes + slab_bytes, 0, 0]
+    else:
+        names = ["zero_kernel", "surface_tri_kernel" if not solid else "solid_tri_kernel",
+                 "surface_coop_kernel" if not solid else "solid_coop_kernel", "-" if not solid else "solid_scan_kernel"]
+        alg_bytes = [slab_bytes, tri_bytes, 0, 2 * slab_bytes if solid else 0]
+        if solid and counters.get("solid_row_lists"):
+            # row-list schedule: no zero-fill (phase 0 is the 64-byte counter reset), the fill writes every table byte once
+            names[0], names[3] = "counter_reset", "solid_fill_kernel"
+            alg_bytes[0], alg_bytes[3] = 0, slab_bytes
     dom = int(np.argmax(phases))
     dom_ms = float(phases[dom])
     achieved = alg_bytes[dom] / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
     step_alg = tri_bytes + slab_bytes
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")       # dram__bytes_read+write per launch from the committed ncu capture
     if os.path.exists(tpath) and world == 1:
         try:
-            traffic = json.load(open(tpath)).get(wname, {}).get(names[dom])
+            tj = json.load(open(tpath))
+            traffic = tj.get(wname, {}).get(names[dom].split(":")[0].strip())
+            traffic_src = tj.get("_source") if traffic is not None else None
         except Exception:
             traffic = None
     roofline = {
         "bound": "hbm", "kernel": names[dom], "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-        "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+        "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
         "kernel_ms": round(dom_ms, 4), "algorithmic_bytes": int(alg_bytes[dom]),
-        "phases_ms": {n: round(float(p), 4) for n, p in zip(names, phases)},
+        "phases_ms": {n: round(float(p), 4) for n, p in zip(names, phases) if n != "-"},
         "step": {"algorithmic_bytes": int(step_alg), "achieved_gbs": round(step_alg / (ms_per_step * 1e-3) / 1e9, 1),
-                 "frac": round(step_alg / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
+                 "frac": round(step_alg / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                 "resident_frac": round(step_alg / (resident_ms * 1e-3) / 1e9 / peak, 4)},
     }
 
     # ---- CPU baseline on this box's host cores (bounded; N=1 only) ---------------------------------
@@ -427,30 +463,54 @@ def run_ours(args):
                         "sample": "first %d of %d triangles, whole %d^3 grid, one run of %.0f ms; threads by calibration %s ms on %d tris (host max %d)"
                                   % (n_sample, len(faces), G, ms, cal, n_cal, max_thr)}
 
+    # ---- second baseline: the reference's OWN GPU kernels (unmodified voxelize.cu / voxelize_solid.cu, sm_100a) on this GPU ----
+    ref_gpu = None
+    if world == 1 and not args.no_ref_gpu:
+        import oracle
+        if oracle.have_ref_gpu():
+            try:
+                rms, rtab = oracle.ref_gpu_run(list(grid.bbox_min), list(grid.bbox_max), G, soup, solid=solid, warmup=2, reps=5, want_table=True)
+                step_ms = rms["mean_ms"] + rms["memset_ms"]
+                ref_gpu = {"value": round(n_tris / step_ms / 1e3, 2), "unit": "Mtri/s", "ms_per_step": round(step_ms, 4),
+                           "kernel_ms": round(rms["mean_ms"], 4), "memset_ms": round(rms["memset_ms"], 4), "popcount": oracle.popcount(rtab),
+                           "kind": "the reference's unmodified voxelize.cu / voxelize_solid.cu built for sm_100a (oracle/_ref/libvoxref_gpu.so), triangles and "
+                                   "table device-resident, CUDA events around its voxelize() call + the table memset it leaves to the caller; "
+                                   "not a parity target (its float path differs from the reference CPU path: see popcount)"}
+            except Exception as exc:
+                ref_gpu = {"unavailable": str(exc)[:200]}
+        else:
+            ref_gpu = {"unavailable": "oracle/_ref/libvoxref_gpu.so not built"}
+
+    timed_region = ("voxb200_mesh_update (caller's triangle order -> tile records, buffers reused: %.3f ms) + %d x voxb200_mesh_voxelize" % (prepare_ms, args.steps)
+                    if mesh is not None else "%d x voxb200_%s on the device soup" % (args.steps, "solid" if solid else "surface"))
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "Mtri/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": w["desc"], "gridsize": G, "triangles": int(n_tris), "mode": "solid" if solid else "surface",
-                   "sharding": "z-slab x%d, triangles routed to the slabs their bbox overlaps, no data-path collective" % world,
-                   "launch": "one captured CUDA graph of the step, replayed K times" if graph is not None else "direct launches",
-                   "triangle_order": ("z-layer order from voxb200_sort_triangles (upload-path option, once per mesh: %.2f ms wall incl. its cudaMalloc, outside the timed "
-                                      "region; e2e uploads and voxelizes the caller's order)" % sort_ms) if sort_ms is not None else "the caller's order",
-                   "l2": "inputs larger than L2 (%.0f MB soup + %.0f MB table slab per GPU vs 126 MB L2)" % (tri_bytes / 1e6, slab_bytes / 1e6)},
+        "config": bench_config(w, n_tris),
+        "details": {"sharding": "z-slab x%d, triangles routed to the slabs their bbox overlaps, no data-path collective" % world,
+                    "launch": "one captured CUDA graph of the step, replayed K times" if graph is not None else "direct launches",
+                    "timed_region": timed_region,
+                    "l2": "inputs larger than L2 (%.0f MB triangles + %.0f MB table slab per GPU vs 126 MB L2)" % (tri_bytes / 1e6, slab_bytes / 1e6),
+                    "mesh_plan": mesh_info},
+        "resident": {"ms_per_step": round(resident_ms, 4), "value": round(n_tris / resident_ms / 1e3, 2), "unit": "Mtri/s",
+                     "note": "the K steps alone, preparation outside"},
+        "prepare_ms": None if prepare_ms is None else round(prepare_ms, 4),
+        "one_shot": one_shot,
         "e2e": {"value": round(n_tris / e2e_ms / 1e3, 2), "unit": "Mtri/s", "h2d_bytes_per_step": e2e_h2d_bytes, "d2h_bytes_per_step": int(slab_bytes),
                 "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall, 3), "steps": e2e_steps,
                 "api": e2e_api + ", per rank", "slab_matches_device_path": e2e_table_check},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "ref_gpu_baseline": ref_gpu,
         "counters": counters, "parity": check,
     }
-    if unsorted is not None:
-        line["unsorted"] = unsorted
     if world > 1:
         line["gather"] = {"ms": round(gather_ms, 4), "bytes_per_rank_received": int(region_bytes * (world - 1)), "how": "NCCL all_gather_into_tensor of the slabs, outside the timed step",
                           "triangles_routed_total": routed_total, "duplication": round(routed_total / n_tris, 4),
                           "route_ms_outside_step": round(route_ms, 3),
                           "note": "the resident input of a rank is the soup routed to its slab (done once at upload, wall-clock above, incl. its cudaMalloc); the e2e number pays for routing every step"}
     print(json.dumps(line), flush=True)
+    if mesh is not None:
+        mesh.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -468,7 +528,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="config4", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-sort", action="store_true", help="keep the caller's triangle order for the resident soup (no voxb200_sort_triangles)")
+    ap.add_argument("--no-ref-gpu", action="store_true", help="skip the reference-GPU-kernel baseline leg")
+    ap.add_argument("--reference-sample", type=int, default=0, help="--impl reference: voxelize only the first N triangles per step (default: the whole mesh)")
+    ap.add_argument("--one-shot", action="store_true", help="time voxb200_surface on the device soup instead of the prepared-mesh path")
     ap.add_argument("--no-graph", action="store_true", help="time direct launches instead of replaying a captured CUDA graph of the step")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -22,7 +22,7 @@ EXPORTS = [
     "voxb200_launch_count", "voxb200_last_counters", "voxb200_version", "voxb200_set_profiling", "voxb200_phase_ms",
     "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release", "voxb200_sort_triangles",
     "voxb200_reference_table_bytes", "voxb200_mesh_create", "voxb200_mesh_create_indexed", "voxb200_mesh_update", "voxb200_mesh_update_indexed",
-    "voxb200_mesh_voxelize", "voxb200_mesh_info", "voxb200_mesh_destroy",
+    "voxb200_mesh_voxelize", "voxb200_mesh_info", "voxb200_mesh_destroy", "voxb200_mesh_counters",
 ]
 
 
@@ -95,6 +95,7 @@ def lib():
     L.voxb200_mesh_voxelize.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
     L.voxb200_mesh_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.voxb200_mesh_destroy.argtypes = [C.c_void_p]
+    L.voxb200_mesh_counters.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
     L.voxb200_launch_count.argtypes = [C.c_int]
     L.voxb200_launch_count.restype = C.c_uint64
     L.voxb200_last_counters.argtypes = [C.POINTER(C.c_uint64)]

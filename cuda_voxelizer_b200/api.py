@@ -280,6 +280,11 @@ class Mesh:
         keys = ("tile_schedule", "tiles", "work_tiles", "instances", "side_triangles", "batches", "zero_quota", "zero_blocks")
         return dict(zip(keys, (int(x) for x in out)))
 
+    def counters(self):
+        out = (C.c_uint64 * 4)()
+        check(_lib.lib().voxb200_mesh_counters(self._h, out))
+        return {"coop_triangles": int(out[0]), "coop_items": int(out[1]), "solid_clamped": int(out[2]), "solid_row_lists": int(out[3])}
+
     def close(self):
         h, self._h = getattr(self, "_h", None), None
         if h and _lib is not None and C is not None:          # (module globals are gone at interpreter exit)

@@ -61,14 +61,21 @@ int grow_dev(T** p, size_t* have, size_t want) {
 	return VOXB200_OK;
 }
 
-bool tileable(const voxb200_mesh& m) {
-	const GridParams& g = m.g;
-	if (m.flags & (VOXB200_SOLID | VOXB200_MORTON)) return false;
+bool tileable(const voxb200_mesh& m) { return voxb::mesh_tileable(m.g, m.flags); }
+
+}  // namespace
+
+namespace voxb {
+bool mesh_tileable(const GridParams& g, unsigned int flags) {
+	if (flags & (VOXB200_SOLID | VOXB200_MORTON)) return false;
 	if (g.G < 256 || g.G > 4096 || (g.G % (g.G < kTileXMax ? 256 : kTileXMax)) != 0 || (g.G < kTileXMax && (g.G & (g.G - 1)) != 0)) return false;
 	if (g.rx0 != 0 || g.rx1 != g.G || g.ry0 != 0 || g.ry1 != g.G) return false;
 	if ((g.rz0 % kTileZ) != 0 || (g.rz1 % kTileZ) != 0) return false;
 	return true;
 }
+}  // namespace voxb
+
+namespace {
 
 // (Re)builds the handle's device state from a triangle source: a 9-float device soup, or device vertices + faces.
 int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const int* d_faces, cudaStream_t st) {
@@ -283,6 +290,19 @@ int voxb200_mesh_info(const voxb200_mesh* m, uint64_t out[8]) {
 		out[1] = m->plan.geom.n_tiles; out[2] = m->plan.n_work; out[3] = m->host_totals[kPlanInstances];
 		out[4] = m->n_side; out[5] = m->host_totals[kPlanBatches]; out[6] = m->plan.zero_quota; out[7] = m->plan.n_zero_blocks;
 	}
+	return VOXB200_OK;
+}
+
+int voxb200_mesh_counters(const voxb200_mesh* m, uint64_t out[4]) {
+	if (!m || !out) return abi_fail(VOXB200_EINVAL, "NULL pointer");
+	int rc = check_device(m);
+	if (rc) return rc;
+	unsigned long long c[kNumCounters];
+	CU(cudaMemcpy(c, m->ws.counters, sizeof(c), cudaMemcpyDeviceToHost));
+	out[0] = c[kCtrQueue] >> 32;
+	out[1] = c[kCtrQueueOverflow] ? ~0ull : (c[kCtrQueue] & 0xffffffffull);
+	out[2] = c[kCtrSolidClamp];
+	out[3] = m->ws.last_row_lists ? 1 : 0;
 	return VOXB200_OK;
 }
 

@@ -330,10 +330,6 @@ __device__ __forceinline__ void zero_chunk_at(const GridParams& g, const TilePla
 	const unsigned int word = base + ((row / (unsigned int)kTileY) * (unsigned int)g.G + (row % (unsigned int)kTileY)) * Gw + 4u * ((unsigned int)lane & ((1u << lanes_shift) - 1u));
 	*reinterpret_cast<uint4*>(table + word) = make_uint4(0u, 0u, 0u, 0u);
 }
-__device__ __forceinline__ void zero_chunk(const GridParams& g, const TilePlan& p, unsigned int* __restrict__ table, unsigned int c, int lane) {
-	zero_chunk_at(g, p, table, __ldg(p.empty + (c >> p.geom.chunk_shift)), c, lane);
-}
-
 #ifndef VOXB_RED_BLOCK
 #define VOXB_RED_BLOCK 128
 #endif
@@ -364,7 +360,13 @@ __global__ void __launch_bounds__(kRedBlock, WIDE ? 4 : VOXB_RED_MINB) surface_t
 		// the part of the empty space that is not cleared by the tile blocks below
 		const unsigned int c0 = p.zero_rest_first + blockIdx.x * (unsigned int)kZeroBlockChunks;
 		const unsigned int c1 = min(p.zero_chunks, c0 + (unsigned int)kZeroBlockChunks);
-		for (unsigned int c = c0 + warp; c < c1; c += kRedBlock / 32) zero_chunk(g, p, table, c, lane);
+		unsigned int cur = ~0u, base = 0u;             // the tile address is loaded once per tile, so the stores do not wait on it
+#pragma unroll 4
+		for (unsigned int c = c0 + warp; c < c1; c += kRedBlock / 32) {
+			const unsigned int tile = c >> p.geom.chunk_shift;
+			if (tile != cur) { base = __ldg(p.empty + tile); cur = tile; }
+			zero_chunk_at(g, p, table, base, c, lane);
+		}
 		return;
 	}
 	const uint4 wk = __ldg(p.work + (blockIdx.x - p.n_zero_blocks));       // {tile's first table word, records, first record, batches before}

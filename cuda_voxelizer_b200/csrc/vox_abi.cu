@@ -24,6 +24,8 @@ struct HostPath {
 	float* d_verts = nullptr; size_t verts_bytes = 0;
 	int* d_faces = nullptr; size_t faces_bytes = 0;
 	void* pinned[2] = {nullptr, nullptr}; size_t pinned_bytes = 0;
+	voxb200_mesh* mesh = nullptr;           // prepared mesh of voxb200_voxelize_host_indexed (tile schedule), re-prepared per call
+	voxb200_grid mesh_grid{}; voxb200_region mesh_region{}; bool mesh_has_region = false;
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	cudaEvent_t buf_free[2] = {nullptr, nullptr};
@@ -652,26 +654,50 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 	if (rc) return rc;
 	const size_t n_faces = grid->n_triangles;
 	const size_t table_bytes = region_words * sizeof(unsigned int);
+	// Surface, linear order, tileable grid: the upload path bins the faces straight into the tile records of a prepared mesh (no
+	// intermediate soup) and the tile-owner kernel writes the table; everything else expands to a soup and runs the one-shot kernels.
+	const bool tiles = mesh_tileable(g, flags & (VOXB200_SOLID | VOXB200_MORTON)) && n_faces > 0;
 	if ((rc = grow(&hp.d_verts, &hp.verts_bytes, n_verts * 3 * sizeof(float)))) return rc;
 	if ((rc = grow(&hp.d_faces, &hp.faces_bytes, n_faces * 3 * sizeof(int) + 16))) return rc;
-	if ((rc = grow(&hp.d_tris, &hp.tris_bytes, n_faces * 9 * sizeof(float) + 16))) return rc;
+	if (!tiles && (rc = grow(&hp.d_tris, &hp.tris_bytes, n_faces * 9 * sizeof(float) + 16))) return rc;
 	if ((rc = grow(&hp.d_table, &hp.table_bytes, table_bytes))) return rc;
 	cudaStream_t st = hp.stream;
 	CU(cudaEventRecord(hp.ev[0], st));
 	rc = h2d(hp, hp.d_verts, host_verts, n_verts * 3 * sizeof(float), st);
 	if (!rc) rc = h2d(hp, hp.d_faces, host_faces, n_faces * 3 * sizeof(int), st);
 	if (rc) return rc;
-	cudaError_t e = launch_expand_indexed(hp.d_verts, hp.d_faces, n_faces, n_verts, false, hp.d_tris, st);
-	if (e != cudaSuccess) return fail_cuda(e, "expand_indexed");
-	CU(cudaEventRecord(hp.ev[1], st));
-	rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, flags & VOXB200_MORTON, region, st);
-	if (rc) return rc;
+	if (tiles) {
+		const bool same = hp.mesh && memcmp(&hp.mesh_grid, grid, sizeof(*grid)) == 0 && hp.mesh_has_region == (region != nullptr) &&
+		                  (!region || memcmp(&hp.mesh_region, region, sizeof(*region)) == 0);
+		if (same) {
+			rc = voxb200_mesh_update_indexed(hp.mesh, hp.d_verts, n_verts, hp.d_faces, st);
+		} else {
+			if (hp.mesh) { voxb200_mesh_destroy(hp.mesh); hp.mesh = nullptr; }
+			rc = voxb200_mesh_create_indexed(grid, hp.d_verts, n_verts, hp.d_faces, 0u, region, &hp.mesh, st);
+			if (!rc) { hp.mesh_grid = *grid; hp.mesh_has_region = region != nullptr; if (region) hp.mesh_region = *region; }
+		}
+		if (rc) return rc;
+		CU(cudaEventRecord(hp.ev[1], st));
+		rc = voxb200_mesh_voxelize(hp.mesh, hp.d_table, 0u, st);
+		if (rc) return rc;
+	} else {
+		cudaError_t e = launch_expand_indexed(hp.d_verts, hp.d_faces, n_faces, n_verts, false, hp.d_tris, st);
+		if (e != cudaSuccess) return fail_cuda(e, "expand_indexed");
+		CU(cudaEventRecord(hp.ev[1], st));
+		rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, flags & VOXB200_MORTON, region, st);
+		if (rc) return rc;
+	}
 	CU(cudaEventRecord(hp.ev[2], st));
 	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));
 	CU(cudaEventRecord(hp.ev[3], st));
 	unsigned long long overflow = 0ull;
-	CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
+	if (!tiles) CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
 	CU(cudaStreamSynchronize(st));
+	if (tiles) {
+		uint64_t c[4];
+		if ((rc = voxb200_mesh_counters(hp.mesh, c))) return rc;
+		overflow = c[1] == ~0ull;
+	}
 	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
 	if (timing_ms) {
 		CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
@@ -715,6 +741,7 @@ int voxb200_release(void) {
 	Workspace& ws = g_ws[dev];
 	HostPath& hp = g_hp[dev];
 	if (ws.device == dev) CU(cudaDeviceSynchronize());
+	if (hp.mesh) { voxb200_mesh_destroy(hp.mesh); hp.mesh = nullptr; }
 	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch, ws.row_count, ws.row_marks,
 	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces};
 	for (void* p : dev_ptrs) if (p) cudaFree(p);

@@ -146,6 +146,7 @@ cudaError_t launch_tile_plan(const TileGeom& tg, unsigned int cap, const unsigne
 cudaError_t launch_tile_scatter(const GridParams& g, const TileGeom& tg, unsigned int cap, const float* d_soup, const float* d_verts,
                                 const int* d_faces, const unsigned int* d_keys, const unsigned int* d_cnt, const unsigned int* d_off,
                                 unsigned int* d_fill, void* d_records, float* d_side, unsigned long long* d_totals, cudaStream_t st);
+bool mesh_tileable(const GridParams& g, unsigned int flags);      // mesh.cu: the tile schedule covers this grid / region / mode
 cudaError_t launch_surface_tiles(const GridParams& g, const TilePlan& p, unsigned int* d_table, bool accumulate, cudaStream_t st);
 
 // ---- shared by the ABI translation units (defined in vox_abi.cu) ---------------------------------------------

@@ -216,6 +216,8 @@ int voxb200_mesh_update(voxb200_mesh* mesh, const float* d_tris9, void* stream);
 int voxb200_mesh_update_indexed(voxb200_mesh* mesh, const float* d_verts, size_t n_verts, const int32_t* d_faces, void* stream);
 int voxb200_mesh_voxelize(voxb200_mesh* mesh, unsigned int* d_table, unsigned int flags, void* stream);
 int voxb200_mesh_info(const voxb200_mesh* mesh, uint64_t out[8]);
+/* voxb200_last_counters for the mesh's last voxelization (its private workspace); synchronises the device. */
+int voxb200_mesh_counters(const voxb200_mesh* mesh, uint64_t out[4]);
 int voxb200_mesh_destroy(voxb200_mesh* mesh);
 
 /*
