@@ -291,3 +291,31 @@ class Mesh:
             _lib.lib().voxb200_mesh_destroy(h)
 
     __del__ = close
+
+
+def voxelize_host_multi(grid, host_verts, host_faces, host_table=None, solid=False, morton=False, devices=None, n_devices=None):
+    """One process, N GPUs (voxb200_voxelize_host_multi): indexed mesh and table in host memory (numpy, or pinned torch CPU
+    tensors for full speed).  Returns (table, timing_ms[h2d, peer gather, prepare, voxelize, d2h, total, wall, n])."""
+    def ptr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+    n_verts = (host_verts.numel() if hasattr(host_verts, "numel") else host_verts.size) // 3
+    if devices is None:
+        devices = list(range(n_devices if n_devices is not None else device_count()))
+    if host_table is None:
+        host_table = np.empty(table_bytes(grid.gridsize[0]) // 4, np.uint32)
+    arr = (C.c_int * len(devices))(*devices)
+    timing = (C.c_float * 8)()
+    flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+    check(_lib.lib().voxb200_voxelize_host_multi(C.byref(grid), C.c_void_p(ptr(host_verts)), n_verts, C.c_void_p(ptr(host_faces)),
+                                                 C.c_void_p(ptr(host_table)), flags, arr, len(devices), timing))
+    return host_table, [float(t) for t in timing]
+
+
+def gather_slabs(slabs, devices, out, out_device, stream=None):
+    """voxb200_gather_slabs: device-resident slabs (CUDA tensors, region order) -> one CUDA tensor `out` on `out_device`."""
+    n = len(slabs)
+    ptrs = (C.c_void_p * n)(*[s.data_ptr() for s in slabs])
+    devs = (C.c_int * n)(*devices)
+    sizes = (C.c_size_t * n)(*[s.numel() * s.element_size() for s in slabs])
+    check(_lib.lib().voxb200_gather_slabs(ptrs, devs, sizes, n, C.c_void_p(out.data_ptr()), int(out_device), _stream_ptr(stream)))
+    return out

@@ -742,6 +742,7 @@ int voxb200_release(void) {
 	HostPath& hp = g_hp[dev];
 	if (ws.device == dev) CU(cudaDeviceSynchronize());
 	if (hp.mesh) { voxb200_mesh_destroy(hp.mesh); hp.mesh = nullptr; }
+	multi_release_device(dev);
 	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch, ws.row_count, ws.row_marks,
 	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces};
 	for (void* p : dev_ptrs) if (p) cudaFree(p);

@@ -155,6 +155,7 @@ int abi_fail_cuda(cudaError_t e, const char* what);
 int abi_current_ws(Workspace** out);                 // the calling thread's current device's library workspace
 int abi_init_workspace(Workspace& ws, int dev);      // a private workspace (prepared meshes own one each)
 void abi_free_workspace(Workspace& ws);
+void multi_release_device(int dev);                 // multi.cu
 }  // namespace voxb
 struct voxb200_grid;
 struct voxb200_region;

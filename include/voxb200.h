@@ -25,6 +25,7 @@
  *   voxb200_solid ........................ voxelize_solid()               src/voxelize_solid.cu:147-193 (kernel :73-145)
  *   voxb200_morton_encode ................ mortonEncode_LUT()             src/voxelize.cuh:20-34
  *   voxb200_voxelize_host ................ main.cpp:203-222 (upload + voxelize + table read-back by the writers)
+ *   voxb200_voxelize_host_multi .......... main.cpp:203-222 with N GPUs (new: the reference is single-GPU)
  *   voxb200_mesh_* ....................... (new) prepared mesh for repeated voxelization (README.md:74 "per-frame")
  *   bit-table layout ..................... setBit / checkVoxel            src/voxelize.cu:50-55, src/util.h:25-38
  */
@@ -186,6 +187,29 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
  */
 int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]);
+
+/* ---- multi-GPU: one process, one host thread per device ------------------------------------------------------ */
+/*
+ * The reference's caller is a single-threaded main() that holds the indexed mesh and wants the table in host memory
+ * (main.cpp:203-222).  This serves that caller with n_devices GPUs of one box (devices[] = CUDA ordinals, NULL = 0..n-1):
+ * every device copies 1/N of the mesh bytes over its own PCIe link, the shares are all-gathered device to device
+ * (cudaMemcpyPeerAsync: NVLink where peer access exists), device d voxelizes region d of voxb200_partition(G, morton, d, N) —
+ * disjoint slices of the table, no reduction — and copies its slab straight into its byte range of host_table
+ * (voxb200_table_bytes(G) bytes, pinned for full speed: voxb200_host_alloc).  Synchronous.  flags: VOXB200_SOLID, VOXB200_MORTON.
+ * The table is bit-identical to the single-GPU table.  timing_ms (when non-NULL), device milliseconds, maximum over the
+ * devices: [0] H2D of the shares, [1] peer all-gather, [2] preparation (tile records / expansion), [3] voxelization,
+ * [4] D2H of the slab, [5] first H2D byte to last D2H byte; [6] host wall-clock of the call, [7] n_devices.
+ * Linear order needs G*G divisible by 32 for N > 1; morton order a power-of-two N <= 8.
+ */
+int voxb200_voxelize_host_multi(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
+                                unsigned int* host_table, unsigned int flags, const int* devices, int n_devices, float timing_ms[8]);
+/* Device-resident slabs (slab k on device slab_devices[k], slab_bytes[k] bytes, in region order) -> one table on table_device:
+ * peer copies enqueued on `stream` (a stream of the current device).  The NCCL-free slab gather of SURVEY §8e. */
+int voxb200_gather_slabs(unsigned int* const* d_slabs, const int* slab_devices, const size_t* slab_bytes, int n_slabs,
+                         unsigned int* d_table, int table_device, void* stream);
+/* Pinned (page-locked, portable) host memory for the host entry points. */
+int voxb200_host_alloc(void** host_ptr, size_t bytes);
+int voxb200_host_free(void* host_ptr);
 
 /* ---- prepared meshes: the resident / per-frame interface ------------------------------------------------ */
 /*
