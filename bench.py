@@ -346,7 +346,20 @@ def run_ours(args):
         torch.cuda.synchronize()
         e2e_wall_ms = (time.perf_counter() - t0) * 1e3
         e2e_h2d_bytes = int(pinned_verts.numel() * 4 + pinned_faces.numel() * 4)
-    e2e_api = "voxb200_voxelize_host_indexed (pinned host vertices+faces -> H2D -> tile records / expand -> voxelize -> D2H table slab)"
+        e2e_phases = dict(zip(("h2d", "prepare_voxelize", "readback"), (round(float(x), 3) for x in ms[:3])))
+        e2e_readback = vb.last_readback()
+        # the same call with the plain dense copy of the table, for comparison
+        vb.set_readback_mode("dense")
+        vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)
+        dense_ms = 0.0
+        for _ in range(max(1, e2e_steps // 2)):
+            _, ms = vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)
+            dense_ms += ms[3]
+        e2e_dense_ms = dense_ms / max(1, e2e_steps // 2)
+        vb.set_readback_mode("auto")
+        vb.voxelize_host_indexed(grid, pinned_verts, pinned_faces, pinned_table, solid=solid, region=region_arg)      # the table the checks below read
+    e2e_api = ("voxb200_voxelize_host_indexed (pinned host vertices+faces -> H2D -> tile records / expand -> voxelize -> table in pinned host memory: "
+               "dense D2H, or non-zero words + host-thread expansion when the table is sparse)")
     if world > 1:
         # N > 1: the upload is sharded too.  Rank r holds 1/N of the soup in pinned memory, uploads only that, routes it
         # on the GPU to the N slabs, swaps triangles in one all-to-all over NVLink, voxelizes its slab, reads it back.
@@ -508,6 +521,14 @@ def run_ours(args):
     e2e_obj = {"value": round(n_tris / e2e_ms / 1e3, 2), "unit": "Mtri/s", "h2d_bytes_per_step": e2e_h2d_bytes, "d2h_bytes_per_step": int(slab_bytes),
                "ms_per_step": round(e2e_ms, 3), "wall_ms_per_step": round(e2e_wall, 3), "steps": e2e_steps,
                "api": e2e_api + ", per rank", "slab_matches_device_path": e2e_table_check}
+    if world == 1:
+        # bytes that crossed the link device -> host: the dense table, or the {index, value} pairs + the per-block prefix
+        if e2e_readback["sparse"]:
+            e2e_obj["d2h_bytes_per_step"] = int(8 * e2e_readback["nonzero_words"] + 8 * (slab_bytes // 8192 + 1))
+        e2e_obj.update({"host_table_bytes": int(slab_bytes), "phases_ms": e2e_phases,
+                        "readback": dict(e2e_readback, mode="sparse" if e2e_readback["sparse"] else "dense", host_threads=os.environ.get("VOXB200_HOST_THREADS", "default (half the hardware threads, <= 16)")),
+                        "dense_readback": {"ms_per_step": round(e2e_dense_ms, 3), "value": round(n_tris / e2e_dense_ms / 1e3, 2), "d2h_bytes_per_step": int(slab_bytes)},
+                        "host_table_matches_device_table": bool(torch.equal(pinned_table, table.cpu()))})
     if multi is not None:
         # the headline e2e at N > 1 is the C-ABI call a C++ caller makes; the torch.distributed path is kept beside it
         import oracle

@@ -156,6 +156,30 @@ def download(buf_ptr, nbytes, stream=0):
     return out
 
 
+def download_table(d_table, host_table, stream=None):
+    """voxb200_download_table: CUDA tensor -> host array (numpy, or a pinned torch CPU tensor for full speed); sparse read-back
+    when it pays.  Returns (host_table, {"sparse": bool, "nonzero_words": int})."""
+    info = (C.c_uint64 * 2)()
+    hp = host_table.data_ptr() if hasattr(host_table, "data_ptr") else host_table.ctypes.data
+    check(_lib.lib().voxb200_download_table(C.c_void_p(d_table.data_ptr()), d_table.numel(), C.c_void_p(hp), _stream_ptr(stream), info))
+    return host_table, {"sparse": bool(info[0]), "nonzero_words": int(info[1])}
+
+
+def set_readback_mode(mode):
+    """'auto' | 'dense' | 'sparse' (voxb200_set_readback_mode)."""
+    check(_lib.lib().voxb200_set_readback_mode({"auto": 0, "dense": 1, "sparse": 2}[mode]))
+
+
+def set_host_threads(n):
+    check(_lib.lib().voxb200_set_host_threads(int(n)))
+
+
+def last_readback():
+    info = (C.c_uint64 * 2)()
+    check(_lib.lib().voxb200_last_readback(info))
+    return {"sparse": bool(info[0]), "nonzero_words": int(info[1])}
+
+
 def launch_count(reset=False):
     return int(_lib.lib().voxb200_launch_count(int(reset)))
 

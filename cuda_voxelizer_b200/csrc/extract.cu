@@ -89,6 +89,61 @@ __global__ void __launch_bounds__(kExtBlock) extract_write_kernel(const unsigned
 	}
 }
 
+// ---- non-zero WORDS of the table as {word index, value} pairs, ascending: the sparse read-back of readback.cu ----------------
+// Same three passes as above (count per 8 KB block, scan, write); a thread owns 8 consecutive words = two 16-byte loads.
+__global__ void __launch_bounds__(kExtBlock) nz_count_kernel(const uint4* __restrict__ table, size_t n_words, unsigned int* __restrict__ block_counts) {
+	__shared__ unsigned int smem[kExtBlock / 32];
+	const size_t first = (size_t)blockIdx.x * kExtBlockWords + (size_t)threadIdx.x * kExtWords;
+	unsigned int c = 0;
+	if (first + kExtWords <= n_words) {
+		const uint4 a = __ldg(table + first / 4), b = __ldg(table + first / 4 + 1);
+		c = (a.x != 0u) + (a.y != 0u) + (a.z != 0u) + (a.w != 0u) + (b.x != 0u) + (b.y != 0u) + (b.z != 0u) + (b.w != 0u);
+	} else {
+		const unsigned int* t = reinterpret_cast<const unsigned int*>(table);
+		for (int k = 0; k < kExtWords; k++) if (first + k < n_words) c += __ldg(t + first + k) != 0u;
+	}
+	unsigned int excl;
+	const unsigned int total = block_sum(c, smem, excl);
+	if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(kExtBlock) nz_write_kernel(const uint4* __restrict__ table, size_t n_words, const unsigned long long* __restrict__ offsets,
+                                                             uint2* __restrict__ out) {
+	__shared__ unsigned int smem[kExtBlock / 32];
+	const size_t first = (size_t)blockIdx.x * kExtBlockWords + (size_t)threadIdx.x * kExtWords;
+	unsigned int w[kExtWords], c = 0;
+	if (first + kExtWords <= n_words) {
+		const uint4 a = __ldg(table + first / 4), b = __ldg(table + first / 4 + 1);
+		w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w; w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+	} else {
+		const unsigned int* t = reinterpret_cast<const unsigned int*>(table);
+#pragma unroll
+		for (int k = 0; k < kExtWords; k++) w[k] = first + k < n_words ? __ldg(t + first + k) : 0u;
+	}
+#pragma unroll
+	for (int k = 0; k < kExtWords; k++) c += w[k] != 0u;
+	unsigned int excl;
+	const unsigned int total = block_sum(c, smem, excl);
+	if (total == 0u) return;
+	uint2* o = out + offsets[blockIdx.x] + excl;
+#pragma unroll
+	for (int k = 0; k < kExtWords; k++) if (w[k]) *o++ = make_uint2((unsigned int)(first + k), w[k]);
+}
+cudaError_t launch_nz_count(const unsigned int* d_table, size_t n_words, unsigned int* d_counts, unsigned long long* d_offsets, cudaStream_t st) {
+	const size_t blocks = (n_words + kExtBlockWords - 1) / kExtBlockWords;
+	if (blocks == 0) return cudaSuccess;
+	nz_count_kernel<<<(unsigned)blocks, kExtBlock, 0, st>>>(reinterpret_cast<const uint4*>(d_table), n_words, d_counts);
+	extract_scan_kernel<<<1, 1024, 0, st>>>(d_counts, d_offsets, blocks);
+	g_launch_count += 2;
+	return cudaGetLastError();
+}
+cudaError_t launch_nz_write(const unsigned int* d_table, size_t n_words, const unsigned long long* d_offsets, void* d_pairs, cudaStream_t st) {
+	const size_t blocks = (n_words + kExtBlockWords - 1) / kExtBlockWords;
+	if (blocks == 0) return cudaSuccess;
+	nz_write_kernel<<<(unsigned)blocks, kExtBlock, 0, st>>>(reinterpret_cast<const uint4*>(d_table), n_words, d_offsets, reinterpret_cast<uint2*>(d_pairs));
+	g_launch_count++;
+	return cudaGetLastError();
+}
+
 cudaError_t launch_extract_count(const unsigned int* d_table, size_t n_words, unsigned int* d_counts, unsigned long long* d_offsets, cudaStream_t st) {
 	const size_t blocks = (n_words + kExtBlockWords - 1) / kExtBlockWords;
 	if (blocks == 0) return cudaSuccess;

@@ -36,6 +36,7 @@ struct DevState {                       // persistent per device, grown on deman
 	cudaStream_t stream = nullptr;
 	cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	bool peers_enabled[64] = {};
+	Readback rb;                            // slab -> host table (readback.cu)
 };
 DevState g_dev[64];
 
@@ -176,21 +177,29 @@ void worker(Shared& S, int d) {
 		else STEP_RC(voxb200_surface(S.grid, D.d_tris, D.d_table, S.flags & VOXB200_MORTON, region, st));
 	}
 	STEP(cudaEventRecord(D.ev[4], st));
-	// 4. the slab straight into its place in the one host table
-	STEP(cudaMemcpyAsync((char*)S.host_table + S.slab_offset[d], D.d_table, S.slab_bytes[d], cudaMemcpyDeviceToHost, st));
-	STEP(cudaEventRecord(D.ev[5], st));
+	// 4. the slab straight into its place in the one host table: a dense copy, or its non-zero words expanded by this device's share
+	//    of the host threads (readback.cu)
+	STEP(cudaEventSynchronize(D.ev[4]));
+	const auto t_back = std::chrono::steady_clock::now();
+	if (!S.failed) {
+		int threads = readback_default_threads() / S.n;
+		if (threads < 1) threads = 1;
+		STEP_RC(readback_table(D.rb, D.d_table, S.slab_bytes[d] / sizeof(unsigned int), (unsigned int*)((char*)S.host_table + S.slab_offset[d]), st, threads));
+	}
+	const float back_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_back).count();
 	STEP(cudaStreamSynchronize(st));
 	if (!S.failed) {
 		uint64_t c[4] = {0, 0, 0, 0};
 		const int rc = tiles ? voxb200_mesh_counters(D.mesh, c) : voxb200_last_counters(c);
 		if (rc == VOXB200_OK && c[1] == ~0ull) S.fail(VOXB200_EINVAL, "more than 2^32 (y,z) rows / sample blocks queued for the large-triangle path on one device: table contents undefined");
 	}
-	for (int k = 0; k < 5; k++) {
+	for (int k = 0; k < 4; k++) {
 		S.phase_ms[d][k] = 0.0f;
 		if (!S.failed) cudaEventElapsedTime(&S.phase_ms[d][k], D.ev[k], D.ev[k + 1]);
 	}
+	S.phase_ms[d][4] = back_ms;                  // host clock: the copy engine and the host threads both work in this phase
 	S.phase_ms[d][5] = 0.0f;
-	if (!S.failed) cudaEventElapsedTime(&S.phase_ms[d][5], D.ev[0], D.ev[5]);
+	if (!S.failed) { cudaEventElapsedTime(&S.phase_ms[d][5], D.ev[0], D.ev[4]); S.phase_ms[d][5] += back_ms; }
 	cudaGetLastError();
 	S.barrier.arrive_and_wait();                 // nobody's buffers are reused (next call) while a peer may still be reading them
 }
@@ -203,6 +212,7 @@ void multi_release_device(int dev) {
 	if (dev < 0 || dev >= 64) return;
 	DevState& D = g_dev[dev];
 	if (D.mesh) voxb200_mesh_destroy(D.mesh);
+	readback_free(D.rb);
 	for (void* p : {(void*)D.d_verts, (void*)D.d_faces, (void*)D.d_tris, (void*)D.d_table}) if (p) cudaFree(p);
 	if (D.stream) cudaStreamDestroy(D.stream);
 	for (auto& e : D.ev) if (e) cudaEventDestroy(e);

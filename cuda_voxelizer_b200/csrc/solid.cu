@@ -12,7 +12,7 @@
 // Schedule: zero_kernel -> solid_tri_kernel (thread per triangle; triangles with many samples are
 // queued) -> solid_coop_kernel (warp per block of samples of a queued triangle) -> solid_scan_kernel.
 //
-// ROW LISTS (linear order, fresh table, 128 <= G <= 2048): the marks of a row do not need the table at all until the
+// ROW LISTS (linear order, fresh table, 128 <= G <= 4096): the marks of a row do not need the table at all until the
 // fill.  Each accepted sample appends its xmax to a short per-row list (a 32-bit counter + kRowMarks 16-bit slots per
 // (y,z) row, L2-resident: 20 B per row) and solid_fill_kernel builds every row straight from its list — the XOR of the
 // prefix masks [0, xmax] — writing each table byte exactly once: no zero-fill, no cold-DRAM atomics, no read-back.
@@ -28,7 +28,7 @@
 namespace voxb {
 
 constexpr int kBlock = 256;
-constexpr int kSmallSamples = 64;     // (y,z) samples a single thread finishes itself
+constexpr int kSmallSide = 8;         // a thread finishes triangles whose (y,z) sample box is at most 8 x 8 itself
 constexpr int kSamplesPerItem = 256;  // samples per cooperative work item (8 per lane)
 constexpr int kRowMarks = 8;          // listed marks per (y,z) row (one 16-byte vector of 16-bit xmax values)
 
@@ -40,12 +40,20 @@ __device__ __forceinline__ bool clip_samples_to_region(const GridParams& g, Soli
 	return !s.skip && s.y0 <= s.y1 && s.z0 <= s.z1;
 }
 
-// One centre sample (y,z) of one triangle: accept test, xmax, then mark or flip.
+// Row lists: slot `slot` of row `row` (relative to the region) takes the mark; the 9th and later marks of a row go to the overflow
+// table as single bits (the region is a z-slab of whole rows: its words are (x + G * row) / 32).
+__device__ __forceinline__ void row_list_commit(const GridParams& g, const RowLists& rl, unsigned int* __restrict__ overflow,
+                                                unsigned int row, unsigned int slot, unsigned int xmax) {
+	if (slot < (unsigned int)kRowMarks) rl.marks[(size_t)row * kRowMarks + slot] = (unsigned short)xmax;
+	else {
+		const unsigned long long idx = (unsigned long long)xmax + (unsigned long long)g.G * row;
+		atomicXor(overflow + (idx >> 5), 1u << (31u - (unsigned int)(idx & 31ull)));
+	}
+}
+// An ACCEPTED centre sample (y,z) of one triangle: xmax, then mark or flip.
 template <int MODE, bool MORTON>
-__device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams& g, int y, int z,
-                                           unsigned int* __restrict__ table, unsigned long long* __restrict__ counters, const RowLists& rl) {
-	const float py = solid_center(y, g.uy), pz = solid_center(z, g.uz);
-	if (!solid_sample(s, py, pz)) return;
+__device__ __forceinline__ void solid_emit_accepted(const SolidSetup& s, const GridParams& g, int y, int z, float py, float pz,
+                                                    unsigned int* __restrict__ table, unsigned long long* __restrict__ counters, const RowLists& rl) {
 	int xmax = solid_xmax(s, g, py, pz);
 	// The reference leaves xmax unclamped: < 0 wraps to a 2^32-iteration out-of-bounds loop on the CPU,
 	// >= G writes out of bounds.  Skip / clamp instead and count the event.
@@ -54,12 +62,7 @@ __device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams
 	if (MODE == kRowLists) {
 		// `table` is the library's overflow table here
 		const unsigned int row = (unsigned int)y + (unsigned int)g.G * (unsigned int)(z - g.rz0);
-		const unsigned int slot = atomicAdd(rl.count + row, 1u);
-		if (slot < (unsigned int)kRowMarks) rl.marks[(size_t)row * kRowMarks + slot] = (unsigned short)xmax;
-		else {
-			const unsigned long long idx = voxel_index<false>(g, xmax, y, z);
-			atomicXor(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
-		}
+		row_list_commit(g, rl, table, row, atomicAdd(rl.count + row, 1u), (unsigned int)xmax);
 	} else if (MODE == kMarkScan) {
 		const unsigned long long idx = voxel_index<false>(g, xmax, y, z);
 		atomicXor(table + ((idx >> 5) - g.word_base), 1u << (31u - (unsigned int)(idx & 31ull)));
@@ -69,6 +72,14 @@ __device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams
 		for (int x = xa; x <= xb; x++) run.add(table, g, voxel_index<MORTON>(g, x, y, z));
 		run.flush(table);
 	}
+}
+// One centre sample (y,z) of one triangle: accept test, then the above.
+template <int MODE, bool MORTON>
+__device__ __forceinline__ void solid_emit(const SolidSetup& s, const GridParams& g, int y, int z,
+                                           unsigned int* __restrict__ table, unsigned long long* __restrict__ counters, const RowLists& rl) {
+	const float py = solid_center(y, g.uy), pz = solid_center(z, g.uz);
+	if (!solid_sample(s, py, pz)) return;
+	solid_emit_accepted<MODE, MORTON>(s, g, y, z, py, pz, table, counters, rl);
 }
 
 template <int MODE, bool MORTON, bool SOA4>
@@ -90,20 +101,56 @@ __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, c
 	SolidSetup s;
 	bool live = false, big = false;
 	unsigned int items = 0u;
+	int ny = 0, nz = 0;
 	if (valid) {
 		shift_tri(t, g);
 		solid_setup(t, g, s);
 		live = clip_samples_to_region(g, s);
 		if (live) {
-			const long long samples = (long long)(s.y1 - s.y0 + 1) * (long long)(s.z1 - s.z0 + 1);
-			big = samples > kSmallSamples;
-			items = (unsigned int)((samples + kSamplesPerItem - 1) / kSamplesPerItem);
+			ny = s.y1 - s.y0 + 1; nz = s.z1 - s.z0 + 1;
+			big = ny > kSmallSide || nz > kSmallSide;
+			items = (unsigned int)(((long long)ny * (long long)nz + kSamplesPerItem - 1) / kSamplesPerItem);
 		}
 	}
 	enqueue_warp(live && big, items, (unsigned int)i, q);
 	if (!live || big) return;
-	for (int y = s.y0; y <= s.y1; y++)
-		for (int z = s.z0; z <= s.z1; z++) solid_emit<MODE, MORTON>(s, g, y, z, table, counters, rl);
+	// Phase 1: the accept test of every sample of the (at most 8 x 8) box, outcomes kept as bit 8 (y - y0) + (z - z0): a short
+	// loop body the warp runs together.  Phase 2: xmax and the list append / flips of the accepted samples only — a triangle of a
+	// closed mesh owns few of its box's samples, and a warp that entered the emission once per sample ran it with a few lanes.
+	unsigned long long acc = 0ull;
+	for (int dy = 0; dy < ny; dy++) {
+		const float py = solid_center(s.y0 + dy, g.uy);
+		unsigned int row = 0u;
+		for (int dz = 0; dz < nz; dz++)
+			if (solid_sample(s, py, solid_center(s.z0 + dz, g.uz))) row |= 1u << dz;
+		acc |= (unsigned long long)row << (8 * dy);
+	}
+	if (MODE == kRowLists) {
+		// the append's returning atomicAdd is a round trip to L2: the slot store of one sample is issued after the NEXT sample's
+		// atomic, so the trip overlaps the next xmax instead of stalling the thread
+		unsigned int pend_row = 0u, pend_slot = 0u, pend_x = 0u;
+		bool pend = false;
+		while (acc) {
+			const int k = __ffsll((long long)acc) - 1;
+			acc &= acc - 1ull;
+			const int y = s.y0 + (k >> 3), z = s.z0 + (k & 7);
+			int xmax = solid_xmax(s, g, solid_center(y, g.uy), solid_center(z, g.uz));
+			if (xmax < 0) { atomicAdd(counters + kCtrSolidClamp, 1ull); continue; }           // as solid_emit_accepted
+			if (xmax > g.G - 1) { atomicAdd(counters + kCtrSolidClamp, 1ull); xmax = g.G - 1; }
+			const unsigned int row = (unsigned int)y + (unsigned int)g.G * (unsigned int)(z - g.rz0);
+			const unsigned int slot = atomicAdd(rl.count + row, 1u);
+			if (pend) row_list_commit(g, rl, table, pend_row, pend_slot, pend_x);
+			pend_row = row; pend_slot = slot; pend_x = (unsigned int)xmax; pend = true;
+		}
+		if (pend) row_list_commit(g, rl, table, pend_row, pend_slot, pend_x);
+		return;
+	}
+	while (acc) {
+		const int k = __ffsll((long long)acc) - 1;
+		acc &= acc - 1ull;
+		const int y = s.y0 + (k >> 3), z = s.z0 + (k & 7);
+		solid_emit_accepted<MODE, MORTON>(s, g, y, z, solid_center(y, g.uy), solid_center(z, g.uz), table, counters, rl);
+	}
 }
 
 template <int MODE, bool MORTON, bool SOA4>
@@ -136,11 +183,11 @@ __global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, 
 	}
 }
 
+// (Both scan kernels also run in place, marks == out: no __restrict__, no read-only loads.)
 // Suffix-XOR along x of every row, one lane per word: rows of `seg` = G/32 <= 32 words (a power of two).  Used for
 // G = 32, 64 (rows shorter than 16 bytes) and as the fallback when a table pointer is not 16-byte aligned.
 template <bool XOR_INTO>
-__global__ void __launch_bounds__(kBlock) solid_scan_narrow_kernel(const unsigned int* __restrict__ marks,
-                                                                   unsigned int* __restrict__ out, size_t n_words, int seg) {
+__global__ void __launch_bounds__(kBlock) solid_scan_narrow_kernel(const unsigned int* marks, unsigned int* out, size_t n_words, int seg) {
 	const size_t at = (size_t)blockIdx.x * kBlock + threadIdx.x;
 	const int pos = (int)(threadIdx.x & 31) & (seg - 1);
 	const unsigned int w = at < n_words ? marks[at] : 0u;
@@ -162,8 +209,7 @@ __global__ void __launch_bounds__(kBlock) solid_scan_narrow_kernel(const unsigne
 // kScanUnroll independent row groups per thread keep enough 16-byte requests in flight to stream at HBM speed.
 constexpr int kScanUnroll = 4;
 template <bool XOR_INTO>
-__global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restrict__ marks, uint4* __restrict__ out,
-                                                            size_t n_vec, int lanes_per_row) {
+__global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* marks, uint4* out, size_t n_vec, int lanes_per_row) {
 	const int lane = threadIdx.x & 31;
 	const int width = lanes_per_row;                              // lanes of this warp that share a row (<= 32)
 	const int pos = lane & (width - 1);
@@ -175,7 +221,7 @@ __global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restr
 #pragma unroll
 		for (int u = 0; u < kScanUnroll; u++) {
 			const size_t at = (span0 + u) * 32 + lane;
-			m[u] = at < n_vec ? __ldg(marks + at) : make_uint4(0u, 0u, 0u, 0u);
+			m[u] = at < n_vec ? marks[at] : make_uint4(0u, 0u, 0u, 0u);
 		}
 #pragma unroll
 		for (int u = 0; u < kScanUnroll; u++) {
@@ -207,77 +253,97 @@ __global__ void __launch_bounds__(kBlock) solid_scan_kernel(const uint4* __restr
 }
 
 // ROW LISTS fill: every table byte written once, from the row's list.  A lane owns 4 consecutive words (one 16-byte
-// store); a row is `lanes_per_row` = G/128 <= 16 consecutive lanes of a warp.  Word wi of a row whose marks are m_1..m_n:
-// XOR over the marks of { all ones if wi < m/32; the bits of x = 32 wi .. m (MSB-first) if wi == m/32; 0 otherwise }.
+// store) = 128 voxels; a row is `lanes_per_row` = G/128 <= 32 consecutive lanes of a warp.  The row is the XOR of the prefix
+// masks [0, m] of its marks m, so a lane's 128 voxels are: all ones iff an odd number of marks lie at or beyond the lane's
+// end, XOR the prefix masks of the marks INSIDE the lane's range.  Nearly every lane has no mark inside and few have two, so
+// the kernel counts (one compare per mark), applies at most one in-range mark with three instructions per word, and leaves
+// lanes with several in-range marks to a general loop that the warp only enters when one of its lanes needs it.
+// Slots beyond a row's count hold 0xffff (= -1, a mark that covers nothing), so no slot needs a validity test.
 // Rows that overflowed their list (count > kRowMarks) add the suffix-XOR of their row of the overflow table, which is
-// cleared again on the way.  Counters are reset for the next call.
+// cleared again on the way.  Counters and slots are reset for the next call.
 constexpr int kFillUnroll = 4;
-__global__ void __launch_bounds__(kBlock) solid_fill_kernel(uint4* __restrict__ out, size_t n_vec, int row_shift, const RowLists rl,
+__device__ __forceinline__ int mark_at(const uint4& mk, int i) {            // slot i of a row's list, sign-extended (0xffff = -1: no mark)
+	const unsigned int pair = i < 4 ? (i < 2 ? mk.x : mk.y) : (i < 6 ? mk.z : mk.w);
+	return (i & 1) ? ((int)pair >> 16) : (int)(short)(pair & 0xffffu);
+}
+// n_vec (16-byte pieces of the region) is a multiple of 32 * kFillUnroll (G >= 128 a power of two) and fits 32 bits (G <= 4096).
+__global__ void __launch_bounds__(kBlock) solid_fill_kernel(uint4* __restrict__ out, unsigned int n_vec, int row_shift, const RowLists rl,
                                                             uint4* __restrict__ overflow) {
 	const int lane = threadIdx.x & 31;
 	const int width = 1 << row_shift;                             // lanes per row
 	const int pos = lane & (width - 1);
+	const int lo = pos << 7;                                      // the lane's first x
 	// a warp owns kFillUnroll consecutive 32-lane spans; all their loads are issued before any is used
-	const size_t span0 = (((size_t)blockIdx.x * kBlock + threadIdx.x) >> 5) * (size_t)kFillUnroll;
+	const unsigned int at0 = ((blockIdx.x * (unsigned int)kBlock + threadIdx.x) >> 5) * (unsigned int)(32 * kFillUnroll) + (unsigned int)lane;
+	if (at0 >= n_vec) return;                                     // whole warps only
 	unsigned int cnt[kFillUnroll];
 	uint4 mk[kFillUnroll];
+	uint4* marks4 = reinterpret_cast<uint4*>(rl.marks);
 #pragma unroll
 	for (int u = 0; u < kFillUnroll; u++) {
-		// both loads are independent (slots beyond the count hold stale values that are never looked at)
-		const size_t at = (span0 + u) * 32 + lane;
-		cnt[u] = at < n_vec ? rl.count[at >> row_shift] : 0u;
-		mk[u] = at < n_vec ? __ldg(reinterpret_cast<const uint4*>(rl.marks) + (at >> row_shift)) : make_uint4(0u, 0u, 0u, 0u);
+		const unsigned int row = (at0 + 32u * u) >> row_shift;
+		cnt[u] = rl.count[row];
+		mk[u] = marks4[row];
 	}
+	__syncwarp();                                                 // every lane of a row has its copy before lane 0 of the row resets the list
 #pragma unroll
 	for (int u = 0; u < kFillUnroll; u++) {
-		const size_t at = (span0 + u) * 32 + lane;
-		const bool valid = at < n_vec;
+		const unsigned int at = at0 + 32u * u;
 		const unsigned int c = cnt[u];
-		unsigned int w[4] = {0u, 0u, 0u, 0u};
-		const int n = (int)min(c, (unsigned int)kRowMarks);
-		const int nmax = __reduce_max_sync(0xffffffffu, n);
+		const unsigned int cmax = __reduce_max_sync(0xffffffffu, c);
+		unsigned int w[4];
+		bool fast = cmax <= 2u;                                   // warp-uniform: closed surfaces cross most rows twice
+		if (fast) {
+			const int d0 = mark_at(mk[u], 0) - lo, d1 = mark_at(mk[u], 1) - lo;
+			const bool in0 = (unsigned int)d0 < 128u, in1 = (unsigned int)d1 < 128u;
+			fast = !__any_sync(0xffffffffu, in0 && in1);
+			if (fast) {
+				// all ones iff an odd number of marks lie at or beyond the lane's end; the mark inside, at offset f, covers the first
+				// f - 32 j + 1 bits of word j (word j holds x = lo + 32 j + (0..31), MSB first); f = -256: none
+				const unsigned int fill = ((d0 >= 128) != (d1 >= 128)) ? 0xffffffffu : 0u;
+				const int f = in0 ? d0 : (in1 ? d1 : -256);
 #pragma unroll
-		for (int i = 0; i < kRowMarks; i++) {
-			if (i < nmax) {                                           // warp-uniform
-				const unsigned int pair = i < 4 ? (i < 2 ? mk[u].x : mk[u].y) : (i < 6 ? mk[u].z : mk[u].w);
-				const unsigned int m = (i & 1) ? (pair >> 16) : (pair & 0xffffu);
-				// word j of this lane holds x = 128 pos + 32 j + (0..31), MSB first; the mark covers its first rel + 1 bits,
-				// rel = m - (128 pos + 32 j): an arithmetic right shift of the top bit by min(rel, 31), nothing for rel < 0
-				const int t = i < n ? (int)m - 128 * pos : -1;
+				for (int j = 0; j < 4; j++) w[j] = fill ^ ~__funnelshift_rc(0xffffffffu, 0u, (unsigned int)max(f - 32 * j + 1, 0));
+			}
+		}
+		if (!fast) {
+			// the general form: every listed mark against every word (empty slots cover nothing)
 #pragma unroll
-				for (int j = 0; j < 4; j++) {
-					const int rel = t - 32 * j;
-					const unsigned int v = (unsigned int)((int)0x80000000 >> min(rel, 31));   // compiles to one clamped SHF
-					w[j] ^= rel >= 0 ? v : 0u;
+			for (int j = 0; j < 4; j++) w[j] = 0u;
+#pragma unroll
+			for (int i = 0; i < kRowMarks; i++) {
+				const int t = mark_at(mk[u], i) - lo;
+#pragma unroll
+				for (int j = 0; j < 4; j++) w[j] ^= ~__funnelshift_rc(0xffffffffu, 0u, (unsigned int)max(t - 32 * j + 1, 0));
+			}
+			if (cmax > (unsigned int)kRowMarks) {
+				// surplus marks of overflowed rows: suffix-XOR of their overflow-table row (the other rows of the warp contribute zeros)
+				const bool ovf = c > (unsigned int)kRowMarks;
+				const uint4 o = ovf ? overflow[at] : make_uint4(0u, 0u, 0u, 0u);
+				unsigned int s[4] = {o.x, o.y, o.z, o.w};
+				const unsigned int par = (__popc(s[0]) + __popc(s[1]) + __popc(s[2]) + __popc(s[3])) & 1u;
+				unsigned int suf = par;
+#pragma unroll
+				for (int d = 1; d < 32; d <<= 1) {
+					const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
+					if (d < width && pos + d < width) suf ^= dn;
 				}
+				unsigned int carry = suf ^ par;
+#pragma unroll
+				for (int j = 3; j >= 0; j--) {
+					unsigned int v = s[j];
+					v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
+					if (carry) v = ~v;
+					carry ^= __popc(s[j]) & 1u;
+					w[j] ^= v;
+				}
+				if (ovf) overflow[at] = make_uint4(0u, 0u, 0u, 0u);
 			}
 		}
-		if (__any_sync(0xffffffffu, c > (unsigned int)kRowMarks)) {
-			// surplus marks of overflowed rows: suffix-XOR of their overflow-table row (the other rows of the warp contribute zeros)
-			const bool ovf = c > (unsigned int)kRowMarks;
-			const uint4 o = ovf ? overflow[at] : make_uint4(0u, 0u, 0u, 0u);
-			unsigned int s[4] = {o.x, o.y, o.z, o.w};
-			const unsigned int par = (__popc(s[0]) + __popc(s[1]) + __popc(s[2]) + __popc(s[3])) & 1u;
-			unsigned int suf = par;
-#pragma unroll
-			for (int d = 1; d < 32; d <<= 1) {
-				const unsigned int dn = __shfl_down_sync(0xffffffffu, suf, d);
-				if (d < width && pos + d < width) suf ^= dn;
-			}
-			unsigned int carry = suf ^ par;
-#pragma unroll
-			for (int j = 3; j >= 0; j--) {
-				unsigned int v = s[j];
-				v ^= v << 1; v ^= v << 2; v ^= v << 4; v ^= v << 8; v ^= v << 16;
-				if (carry) v = ~v;
-				carry ^= __popc(s[j]) & 1u;
-				w[j] ^= v;
-			}
-			if (ovf) overflow[at] = make_uint4(0u, 0u, 0u, 0u);
-		}
-		if (valid) {
-			out[at] = make_uint4(w[0], w[1], w[2], w[3]);
-			if (pos == 0 && c != 0u) rl.count[at >> row_shift] = 0u;
+		out[at] = make_uint4(w[0], w[1], w[2], w[3]);
+		if (pos == 0 && c != 0u) {
+			rl.count[at >> row_shift] = 0u;
+			marks4[at >> row_shift] = make_uint4(~0u, ~0u, ~0u, ~0u);
 		}
 	}
 }
@@ -367,9 +433,10 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 	// then permute it into the morton table.
 	const bool via_linear = o.morton && whole && pow2 && g.G >= 32 && g.G <= 4096;
 	const bool scan = (!o.morton && pow2 && g.G >= 32 && g.G <= 4096 && full_xy) || via_linear;
-	// ROW LISTS: linear order into a fresh table whose rows are 1..16 lanes of 16 bytes
-	const bool lists = scan && !via_linear && !o.accumulate && g.G >= 128 && g.G <= 2048 && (region_words & 3u) == 0 &&
-	                   (reinterpret_cast<uintptr_t>(d_table) & 15u) == 0 && region_words / (size_t)(g.G / 32) <= 0xffffffffull;
+	// ROW LISTS: linear order into a fresh table whose rows are 1..32 lanes of 16 bytes
+	const bool lists = scan && !via_linear && !o.accumulate && g.G >= 128 && g.G <= 4096 && (region_words & 3u) == 0 &&
+	                   (reinterpret_cast<uintptr_t>(d_table) & 15u) == 0 && region_words / (size_t)(g.G / 32) <= 0xffffffffull &&
+	                   ((region_words / 4) % (size_t)(32 * kFillUnroll)) == 0 && region_words / 4 <= 0xffffffffull;
 	ws.last_row_lists = lists;
 	if (lists) {
 		const size_t n_rows = region_words / (size_t)(g.G / 32);
@@ -379,6 +446,7 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 		err = cudaMemsetAsync(ws.counters, 0, kNumCounters * sizeof(unsigned long long), st);
 		if (err != cudaSuccess) return err;
 		prof_mark(ws, 1, st);
+		ws.rows_dirty = true;                 // until the fill has been enqueued: it is what restores the lists' between-calls state
 		if (g.n_tris != 0) {
 			err = o.soa4 ? run_solid_marks<kRowLists, false, true>(ws, g, d_tris, ws.scratch, st) : run_solid_marks<kRowLists, false, false>(ws, g, d_tris, ws.scratch, st);
 			if (err != cudaSuccess) return err;
@@ -392,11 +460,12 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 		int row_shift = 0;
 		while ((128 << row_shift) < g.G) row_shift++;                 // lanes (of 16 bytes) per row = G / 128 = 2^row_shift
 		const size_t fill_threads = (((n_vec + 31) / 32 + kFillUnroll - 1) / kFillUnroll) * 32;
-		solid_fill_kernel<<<(unsigned int)((fill_threads + kBlock - 1) / kBlock), kBlock, 0, st>>>(reinterpret_cast<uint4*>(d_table), n_vec, row_shift, rl,
+		solid_fill_kernel<<<(unsigned int)((fill_threads + kBlock - 1) / kBlock), kBlock, 0, st>>>(reinterpret_cast<uint4*>(d_table), (unsigned int)n_vec, row_shift, rl,
 		                                                                                         reinterpret_cast<uint4*>(ws.scratch));
 		g_launch_count++;
 		err = cudaGetLastError();
 		if (err != cudaSuccess) return err;
+		ws.rows_dirty = false;
 		prof_mark(ws, 4, st);
 		if (ws.prof_on) ws.prof_calls++;
 		return cudaSuccess;

@@ -2,6 +2,7 @@
 // upload, region bookkeeping and the launch of the surface / solid paths.  No CPU fallback lives here:
 // every compute entry point fails with VOXB200_ENODEVICE when there is no sm_100 device.
 #include <cmath>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +32,7 @@ struct HostPath {
 	cudaEvent_t buf_free[2] = {nullptr, nullptr};
 	bool buf_busy[2] = {false, false};     // a copy out of pinned[b] may still be in flight
 	int next_buf = 0;
+	Readback rb;                            // device table -> host table (readback.cu)
 };
 HostPath g_hp[kMaxDevices];
 
@@ -272,20 +274,30 @@ cudaError_t ensure_queue(Workspace& ws, size_t entries) {
 cudaError_t ensure_row_lists(Workspace& ws, size_t n_rows, size_t words, cudaStream_t st) {
 	cudaError_t e = ensure_scratch(ws, words);
 	if (e != cudaSuccess) return e;
+	if (ws.rows_dirty) ws.scratch_zero = false;
 	if (!ws.scratch_zero) {
 		e = launch_zero(ws, ws.scratch, ws.scratch_words, st);
 		if (e != cudaSuccess) return e;
 		ws.scratch_zero = true;
 	}
-	if (n_rows <= ws.row_cap) return cudaSuccess;
-	if (ws.row_count) cudaFree(ws.row_count);
-	if (ws.row_marks) cudaFree(ws.row_marks);
-	ws.row_count = nullptr; ws.row_marks = nullptr; ws.row_cap = 0;
-	e = cudaMalloc(&ws.row_count, n_rows * sizeof(unsigned int));
-	if (e == cudaSuccess) e = cudaMalloc(&ws.row_marks, n_rows * 8 * sizeof(unsigned short));
-	if (e == cudaSuccess) e = cudaMemsetAsync(ws.row_count, 0, n_rows * sizeof(unsigned int), st);
-	if (e == cudaSuccess) ws.row_cap = n_rows;
-	return e;
+	if (n_rows > ws.row_cap) {
+		if (ws.row_count) cudaFree(ws.row_count);
+		if (ws.row_marks) cudaFree(ws.row_marks);
+		ws.row_count = nullptr; ws.row_marks = nullptr; ws.row_cap = 0;
+		e = cudaMalloc(&ws.row_count, n_rows * sizeof(unsigned int));
+		if (e == cudaSuccess) e = cudaMalloc(&ws.row_marks, n_rows * 8 * sizeof(unsigned short));
+		if (e != cudaSuccess) return e;
+		ws.row_cap = n_rows;
+		ws.rows_dirty = true;
+	}
+	if (ws.rows_dirty) {
+		// between calls every counter is 0 and every slot holds 0xffff (= -1: a mark that covers nothing); the fill restores that
+		e = cudaMemsetAsync(ws.row_count, 0, ws.row_cap * sizeof(unsigned int), st);
+		if (e == cudaSuccess) e = cudaMemsetAsync(ws.row_marks, 0xff, ws.row_cap * 8 * sizeof(unsigned short), st);
+		if (e != cudaSuccess) return e;
+		ws.rows_dirty = false;
+	}
+	return cudaSuccess;
 }
 cudaError_t ensure_scratch(Workspace& ws, size_t words) {
 	if (words <= ws.scratch_words) return cudaSuccess;
@@ -587,8 +599,20 @@ int voxb200_solid(const voxb200_grid* grid, const float* d_tris, unsigned int* d
 	return run_path(true, grid, d_tris, d_table, flags, region, (cudaStream_t)stream);
 }
 
+// timing of the host entry points: [0] upload, [1] voxelization (device events); [3] the whole call on the host's clock; [2] the
+// rest = the table's way back (dense copy, or compaction + pairs + the host threads' expansion: readback.cu)
+static int host_timing(HostPath& hp, std::chrono::steady_clock::time_point t_call, float timing_ms[4]) {
+	if (!timing_ms) return VOXB200_OK;
+	CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
+	CU(cudaEventElapsedTime(&timing_ms[1], hp.ev[1], hp.ev[2]));
+	timing_ms[3] = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_call).count();
+	timing_ms[2] = timing_ms[3] - timing_ms[0] - timing_ms[1];
+	return VOXB200_OK;
+}
+
 int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, unsigned int* host_table,
                           unsigned int flags, const voxb200_region* region, float timing_ms[4]) {
+	const auto t_call = std::chrono::steady_clock::now();
 	if (!grid || !host_table || (!host_tris9 && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
 	if (flags & VOXB200_TRIS_SOA4) return fail(VOXB200_EINVAL, "voxb200_voxelize_host takes the 9-float soup");
 	Workspace* ws;
@@ -624,23 +648,17 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 	rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, path_flags, region, st);
 	if (rc) return rc;
 	CU(cudaEventRecord(hp.ev[2], st));
-	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));
-	CU(cudaEventRecord(hp.ev[3], st));
 	unsigned long long overflow = 0ull;
 	CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
+	rc = readback_table(hp.rb, hp.d_table, region_words, host_table, st, 0);
+	if (rc) return rc;
 	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
-	if (timing_ms) {
-		CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
-		CU(cudaEventElapsedTime(&timing_ms[1], hp.ev[1], hp.ev[2]));
-		CU(cudaEventElapsedTime(&timing_ms[2], hp.ev[2], hp.ev[3]));
-		CU(cudaEventElapsedTime(&timing_ms[3], hp.ev[0], hp.ev[3]));
-	}
-	return VOXB200_OK;
+	return host_timing(hp, t_call, timing_ms);
 }
 
 int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]) {
+	const auto t_call = std::chrono::steady_clock::now();
 	if (!grid || !host_table || !host_verts || (!host_faces && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
 	Workspace* ws;
 	int rc = current_ws(&ws);
@@ -688,23 +706,38 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 		if (rc) return rc;
 	}
 	CU(cudaEventRecord(hp.ev[2], st));
-	CU(cudaMemcpyAsync(host_table, hp.d_table, table_bytes, cudaMemcpyDeviceToHost, st));
-	CU(cudaEventRecord(hp.ev[3], st));
 	unsigned long long overflow = 0ull;
 	if (!tiles) CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
+	rc = readback_table(hp.rb, hp.d_table, region_words, host_table, st, 0);
+	if (rc) return rc;
 	if (tiles) {
 		uint64_t c[4];
 		if ((rc = voxb200_mesh_counters(hp.mesh, c))) return rc;
 		overflow = c[1] == ~0ull;
 	}
 	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
-	if (timing_ms) {
-		CU(cudaEventElapsedTime(&timing_ms[0], hp.ev[0], hp.ev[1]));
-		CU(cudaEventElapsedTime(&timing_ms[1], hp.ev[1], hp.ev[2]));
-		CU(cudaEventElapsedTime(&timing_ms[2], hp.ev[2], hp.ev[3]));
-		CU(cudaEventElapsedTime(&timing_ms[3], hp.ev[0], hp.ev[3]));
-	}
+	return host_timing(hp, t_call, timing_ms);
+}
+
+int voxb200_last_readback(uint64_t info[2]) {
+	if (!info) return fail(VOXB200_EINVAL, "NULL pointer");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	info[0] = (uint64_t)g_hp[ws->device].rb.last_mode;
+	info[1] = g_hp[ws->device].rb.last_nonzero;
+	return VOXB200_OK;
+}
+
+int voxb200_download_table(const unsigned int* d_table, size_t table_words, unsigned int* host_table, void* stream, uint64_t info[2]) {
+	if (!d_table || !host_table) return fail(VOXB200_EINVAL, "NULL pointer");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	HostPath& hp = g_hp[ws->device];
+	rc = readback_table(hp.rb, d_table, table_words, host_table, (cudaStream_t)stream, 0);
+	if (rc) return rc;
+	if (info) { info[0] = (uint64_t)hp.rb.last_mode; info[1] = hp.rb.last_nonzero; }
 	return VOXB200_OK;
 }
 
@@ -742,6 +775,7 @@ int voxb200_release(void) {
 	HostPath& hp = g_hp[dev];
 	if (ws.device == dev) CU(cudaDeviceSynchronize());
 	if (hp.mesh) { voxb200_mesh_destroy(hp.mesh); hp.mesh = nullptr; }
+	readback_free(hp.rb);
 	multi_release_device(dev);
 	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch, ws.row_count, ws.row_marks,
 	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces};

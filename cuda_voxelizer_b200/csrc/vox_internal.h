@@ -35,6 +35,7 @@ struct Workspace {
 	unsigned int* row_count = nullptr;        // solid row lists: marks per (y,z) row (all-zero between calls) ...
 	unsigned short* row_marks = nullptr;      // ... and kRowMarks 16-bit xmax slots per row
 	size_t row_cap = 0;                       // rows
+	bool rows_dirty = false;                  // a call failed between the mark and fill phases: counters / slots / spill table are re-initialised next time
 	bool last_row_lists = false;              // the last solid call took the row-list schedule (voxb200_last_counters()[3])
 	// optional per-phase timing (voxb200_set_profiling): a ring of event sets, one set per call
 	bool prof_on = false;
@@ -167,6 +168,26 @@ size_t extract_blocks(size_t n_words);
 cudaError_t launch_extract_count(const unsigned int* d_table, size_t n_words, unsigned int* d_counts, unsigned long long* d_offsets, cudaStream_t st);
 cudaError_t launch_extract_write(const unsigned int* d_table, size_t n_words, const unsigned long long* d_offsets, unsigned long long first_voxel,
                                  unsigned long long* d_out, cudaStream_t st);
+// Non-zero words -> ascending {word index, value} pairs (extract.cu); blocks as extract_blocks(), 2048 words each
+constexpr size_t kNzBlockWords = 2048;
+cudaError_t launch_nz_count(const unsigned int* d_table, size_t n_words, unsigned int* d_counts, unsigned long long* d_offsets, cudaStream_t st);
+cudaError_t launch_nz_write(const unsigned int* d_table, size_t n_words, const unsigned long long* d_offsets, void* d_pairs, cudaStream_t st);
+
+// Device table -> host table (readback.cu): a dense copy, or — when few words are non-zero — the non-zero words only, expanded
+// by host threads that stream the zeros themselves.  Per-device persistent buffers.
+struct Readback {
+	unsigned int* d_counts = nullptr; unsigned long long* d_offsets = nullptr; size_t blocks_cap = 0;
+	unsigned long long* h_offsets = nullptr; size_t h_blocks_cap = 0;       // pinned
+	void* d_pairs = nullptr; size_t pairs_cap = 0;                          // pairs
+	void* h_pairs = nullptr; size_t h_pairs_cap = 0;                        // pinned
+	cudaEvent_t* ev = nullptr; int n_ev = 0;
+	// what the last call did
+	int last_mode = 0;                      // 0 dense copy, 1 sparse
+	unsigned long long last_nonzero = 0;    // non-zero words (sparse mode)
+};
+int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsigned int* host_table, cudaStream_t st, int host_threads);
+void readback_free(Readback& rb);
+int readback_default_threads();
 cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);
 
 }  // namespace voxb

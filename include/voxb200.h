@@ -174,8 +174,14 @@ int voxb200_solid(const voxb200_grid* grid, const float* d_tris, unsigned int* d
 /*
  * End to end with HOST buffers: upload the soup, voxelize (surface, or solid with VOXB200_SOLID),
  * copy the table back, synchronise.  host_table must hold voxb200_table_bytes(G) bytes (or the
- * region's bytes when region != NULL).  Fills timing_ms[0..3] (when non-NULL) with device-side
- * milliseconds: H2D, voxelization, D2H, total.
+ * region's bytes when region != NULL).  Fills timing_ms[0..3] (when non-NULL) with milliseconds: [0] H2D and [1]
+ * voxelization (device events), [3] the whole call (host clock), [2] the rest: the table's way back.
+ *
+ * The way back (voxb200_download_table below): a dense copy, or — for a table of at least 32 MB whose non-zero words are
+ * few (a surface table: 3 % on BASELINE config 4) and a 64-byte aligned host_table — the non-zero words only, as
+ * {index, value} pairs in slices, expanded by host threads that stream the zero lines themselves while the next slice is on
+ * the link (VOXB200_HOST_THREADS, default half the hardware threads, at most 16; VOXB200_READBACK=dense|sparse forces a
+ * mode).  host_table is byte-identical to the device table either way.
  */
 int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, unsigned int* host_table,
                           unsigned int flags, const voxb200_region* region, float timing_ms[4]);
@@ -188,6 +194,20 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]);
 
+/*
+ * The read-back alone: d_table (table_words words on the current device, 16-byte aligned for the sparse mode) -> host_table,
+ * synchronous, after everything enqueued on `stream`.  info (when non-NULL): [0] 1 = the sparse mode ran, [1] non-zero words.
+ * Replaces the reference's reliance on managed memory for the writers' G^3 checkVoxel reads (main.cpp:229-253, util.h:25-38).
+ */
+int voxb200_download_table(const unsigned int* d_table, size_t table_words, unsigned int* host_table, void* stream, uint64_t info[2]);
+/* What the last read-back of the current device's host entry points (voxb200_voxelize_host*, voxb200_download_table) did: same info[]. */
+int voxb200_last_readback(uint64_t info[2]);
+/* 0 = choose per table (default; VOXB200_READBACK=dense|sparse sets the initial value), 1 = always the dense copy, 2 = the sparse
+ * mode whenever the pointers allow it.  Process-wide. */
+int voxb200_set_readback_mode(int mode);
+/* Host threads of the sparse read-back: 0 = default (VOXB200_HOST_THREADS, else half the hardware threads, at most 16).  Process-wide. */
+int voxb200_set_host_threads(int n);
+
 /* ---- multi-GPU: one process, one host thread per device ------------------------------------------------------ */
 /*
  * The reference's caller is a single-threaded main() that holds the indexed mesh and wants the table in host memory
@@ -198,7 +218,8 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
  * (voxb200_table_bytes(G) bytes, pinned for full speed: voxb200_host_alloc).  Synchronous.  flags: VOXB200_SOLID, VOXB200_MORTON.
  * The table is bit-identical to the single-GPU table.  timing_ms (when non-NULL), device milliseconds, maximum over the
  * devices: [0] H2D of the shares, [1] peer all-gather, [2] preparation (tile records / expansion), [3] voxelization,
- * [4] D2H of the slab, [5] first H2D byte to last D2H byte; [6] host wall-clock of the call, [7] n_devices.
+ * [4] the slab's way back (host clock: dense copy or sparse read-back, see voxb200_voxelize_host), [5] first H2D byte to the
+ * slab complete in host memory; [6] host wall-clock of the call, [7] n_devices.
  * Linear order needs G*G divisible by 32 for N > 1; morton order a power-of-two N <= 8.
  */
 int voxb200_voxelize_host_multi(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,

@@ -1,0 +1,9 @@
+#!/bin/bash
+# usage: scripts/gpurun_retry.sh <log> <gpurun args...> — retries while the pod answers busy (rc 3)
+log=$1; shift
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" > "$log" 2>&1
+  rc=$?
+  if ! grep -q "status=transient" "$log"; then exit $rc; fi
+  sleep 90
+done

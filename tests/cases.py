@@ -53,6 +53,7 @@ GOLDEN_CASES = [
     ("bunny", 1024, 0, 0), ("bunny", 1024, 0, 1), ("bunny", 1024, 1, 0), ("bunny", 1024, 1, 1),
     ("bunny", 2048, 0, 0),
     ("bunny", 4096, 0, 0),          # 8 GiB table: the largest grid the fast paths cover
+    ("bunny", 2048, 1, 0), ("bunny", 4096, 1, 0),        # solid row lists with 16 and 32 lanes per row
     # --- synthetic watertight meshes at one world unit per voxel
     ("icosphere:16:64", 128, 0, 0), ("icosphere:16:64", 128, 1, 0), ("icosphere:16:64", 128, 1, 1),
     ("icosphere:64:128", 256, 0, 0), ("icosphere:64:128", 256, 0, 1), ("icosphere:64:128", 256, 1, 0),

@@ -180,3 +180,31 @@ def test_no_contracted_packed_arithmetic_in_sass():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.SO_PATH], capture_output=True, text=True, check=True).stdout
     assert " FADD2 " in sass
     assert " FFMA2 " not in sass and " FMUL2 " not in sass
+
+
+def test_readback_host_expansion_rebuilds_the_table(vb):
+    """The host half of the sparse read-back (csrc/readback_host.cpp) runs without a GPU: {word index, value} pairs -> table,
+    every byte written, for both the AVX-512 and the portable path."""
+    from cuda_voxelizer_b200 import _lib
+    L = C.CDLL(_lib.SO_PATH)
+    rng = np.random.default_rng(3)
+    words = 16 * 5000
+    for density in (0.0, 0.001, 0.05, 0.4, 1.0):
+        want = np.zeros(words, np.uint32)
+        idx = np.flatnonzero(rng.random(words) < density)
+        want[idx] = rng.integers(1, 2**32, len(idx), dtype=np.uint64).astype(np.uint32)
+        pairs = np.stack([idx.astype(np.uint32), want[idx]], axis=1).copy()
+        for sym in ("_ZN4voxb21readback_expand_sliceEPjmmPKvmm", "_ZN4voxb26readback_expand_slice_sse2EPjmmPKvmm"):
+            fn = getattr(L, sym)
+            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+            fn.restype = None
+            raw = np.full(words + 32, 0xDEADBEEF, np.uint32)
+            off = (-(raw.ctypes.data // 4)) % 16
+            table = raw[off:off + words]
+            # two slices, cut on a line boundary in the middle of the pairs
+            cut = 16 * 2311
+            pc = int(np.searchsorted(idx, cut))
+            fn(table.ctypes.data, 0, cut, pairs.ctypes.data, 0, pc)
+            fn(table.ctypes.data, cut, words, pairs.ctypes.data, pc, len(idx))
+            assert np.array_equal(table, want), (density, sym)
+            assert raw[off + words] == 0xDEADBEEF and (off == 0 or raw[off - 1] == 0xDEADBEEF)
