@@ -140,6 +140,10 @@ void worker(Shared& S, int d) {
 	size_t vlo, vhi, flo, fhi;
 	share_range(verts_bytes, d, S.n, &vlo, &vhi);
 	share_range(faces_bytes, d, S.n, &flo, &fhi);
+	int back_threads = readback_default_threads() / S.n;
+	if (back_threads < 1) back_threads = 1;
+	unsigned int* host_slab = (unsigned int*)((char*)S.host_table + S.slab_offset[d]);
+	if (!S.failed && !solid) readback_prezero(D.rb, host_slab, S.slab_bytes[d] / sizeof(unsigned int), back_threads);      // see voxb200_voxelize_host
 	STEP(cudaEventRecord(D.ev[0], st));
 	if (vhi > vlo) STEP(cudaMemcpyAsync((char*)D.d_verts + vlo, (const char*)S.host_verts + vlo, vhi - vlo, cudaMemcpyHostToDevice, st));
 	if (fhi > flo) STEP(cudaMemcpyAsync((char*)D.d_faces + flo, (const char*)S.host_faces + flo, fhi - flo, cudaMemcpyHostToDevice, st));
@@ -181,11 +185,8 @@ void worker(Shared& S, int d) {
 	//    of the host threads (readback.cu)
 	STEP(cudaEventSynchronize(D.ev[4]));
 	const auto t_back = std::chrono::steady_clock::now();
-	if (!S.failed) {
-		int threads = readback_default_threads() / S.n;
-		if (threads < 1) threads = 1;
-		STEP_RC(readback_table(D.rb, D.d_table, S.slab_bytes[d] / sizeof(unsigned int), (unsigned int*)((char*)S.host_table + S.slab_offset[d]), st, threads));
-	}
+	STEP_RC(readback_table(D.rb, D.d_table, S.slab_bytes[d] / sizeof(unsigned int), host_slab, st, back_threads));
+	readback_cancel(D.rb);                       // (error paths) nothing writes the caller's table after this call
 	const float back_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_back).count();
 	STEP(cudaStreamSynchronize(st));
 	if (!S.failed) {

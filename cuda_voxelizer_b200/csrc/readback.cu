@@ -10,7 +10,10 @@
 // Dense tables (solid) and small ones take the plain copy.  Either way host_table ends up byte-identical to the device table.
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <functional>
+#include <mutex>
 #include <cstdlib>
 #include <cstring>
 #include <thread>
@@ -22,8 +25,8 @@
 namespace voxb {
 
 // readback_host.cpp
-void readback_expand_slice(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1);
-void readback_expand_slice_sse2(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1);
+void readback_expand_slice(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1, bool lines_only);
+void readback_expand_slice_sse2(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1, bool lines_only);
 
 namespace {
 
@@ -60,6 +63,10 @@ int dense_copy(Readback& rb, const unsigned int* d_table, size_t words, unsigned
 
 }  // namespace
 
+struct ReadbackHost;
+static void settle_prezero(ReadbackHost& H);
+static void delete_host(void* h);
+
 std::atomic<int> g_readback_mode{[] { const char* e = getenv("VOXB200_READBACK"); return !e ? 0 : !strcmp(e, "dense") ? 1 : !strcmp(e, "sparse") ? 2 : 0; }()};
 
 std::atomic<int> g_host_threads{0};
@@ -87,8 +94,139 @@ void readback_free(Readback& rb) {
 	if (rb.h_pairs) cudaFreeHost(rb.h_pairs);
 	for (int k = 0; k < rb.n_ev; k++) cudaEventDestroy(rb.ev[k]);
 	delete[] rb.ev;
+	if (rb.host) delete_host(rb.host);
 	rb = Readback();
 	cudaGetLastError();
+}
+
+// ---- host threads ------------------------------------------------------------------------------------------------------------
+// A few persistent workers per Readback (per device): submit(fn) runs fn(worker) once on every worker, wait() returns when all are
+// back.  The jobs loop over an atomic slice counter themselves.
+class HostPool {
+	std::vector<std::thread> threads_;
+	std::mutex m_;
+	std::condition_variable cv_, cv_done_;
+	std::function<void(int)> job_;
+	unsigned long long generation_ = 0;
+	int running_ = 0;
+	bool stop_ = false;
+	void loop(int w) {
+		unsigned long long seen = 0;
+		for (;;) {
+			std::function<void(int)> job;
+			{
+				std::unique_lock<std::mutex> lk(m_);
+				cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+				if (stop_) return;
+				seen = generation_;
+				job = job_;
+			}
+			job(w);
+			{
+				std::lock_guard<std::mutex> lk(m_);
+				if (--running_ == 0) cv_done_.notify_all();
+			}
+		}
+	}
+public:
+	int size() const { return (int)threads_.size(); }
+	void resize(int n) {
+		if (n == size()) return;
+		shutdown();
+		stop_ = false;
+		for (int w = 0; w < n; w++) threads_.emplace_back([this, w] { loop(w); });
+	}
+	void submit(std::function<void(int)> fn) {            // not re-entrant: wait() first
+		std::lock_guard<std::mutex> lk(m_);
+		job_ = std::move(fn);
+		running_ = size();
+		generation_++;
+		cv_.notify_all();
+	}
+	void wait() {
+		std::unique_lock<std::mutex> lk(m_);
+		cv_done_.wait(lk, [&] { return running_ == 0; });
+	}
+	void shutdown() {
+		{
+			std::unique_lock<std::mutex> lk(m_);
+			cv_done_.wait(lk, [&] { return running_ == 0; });
+			stop_ = true;
+			cv_.notify_all();
+		}
+		for (auto& t : threads_) t.join();
+		threads_.clear();
+	}
+	~HostPool() { shutdown(); }
+};
+
+struct ReadbackHost {
+	HostPool pool;
+	// the pre-zero job of the call in flight
+	bool active = false;
+	unsigned int* table = nullptr;
+	size_t words = 0;
+	int n_slices = 0;
+	std::atomic<int> next{0};
+	std::atomic<bool> cancel{false};
+	std::vector<unsigned char> zeroed;       // per slice; a worker sets its slices' flags before it returns
+};
+
+static void delete_host(void* h) { ReadbackHost* H = static_cast<ReadbackHost*>(h); settle_prezero(*H); delete H; }
+static ReadbackHost& host_of(Readback& rb) {
+	if (!rb.host) rb.host = new ReadbackHost();
+	return *static_cast<ReadbackHost*>(rb.host);
+}
+static int slices_for(size_t blocks) {
+	static const int want = [] { const char* e = getenv("VOXB200_READBACK_SLICES"); const int v = e ? atoi(e) : 64; return v < 1 ? 1 : v > kMaxSlices ? kMaxSlices : v; }();
+	return (int)(blocks < (size_t)want ? blocks : (size_t)want);
+}
+static bool sparse_eligible(const unsigned int* d_table, size_t words, const unsigned int* host_table) {
+	const int force = g_readback_mode.load();
+	const bool ok = words != 0 && (words & 15u) == 0 && words <= 0xffffffffull && (reinterpret_cast<uintptr_t>(host_table) & 63u) == 0 &&
+	                (!d_table || (reinterpret_cast<uintptr_t>(d_table) & 15u) == 0);
+	return ok && force != 1 && (words * sizeof(unsigned int) >= kSparseMinBytes || force == 2);
+}
+// Stops the pre-zero job (if any) and waits for its workers; afterwards H.zeroed says which slices are all-zero.
+static void settle_prezero(ReadbackHost& H) {
+	if (!H.active) return;
+	H.cancel = true;
+	H.pool.wait();
+	H.active = false;
+}
+
+// A host entry point that expects a sparse table calls this before its first copy: the workers start streaming zeros over the host
+// table while the GPU is still busy with the upload and the voxelization; the read-back then only writes the lines that hold
+// non-zero words (and finishes whatever part of the zero-fill was still to do in the same pass as those lines).
+void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads) {
+	static const bool off = getenv("VOXB200_NO_PREZERO") != nullptr;
+	if (off || !sparse_eligible(nullptr, words, host_table)) return;
+	ReadbackHost& H = host_of(rb);
+	settle_prezero(H);
+	const int T = host_threads > 0 ? host_threads : readback_default_threads();
+	H.pool.resize(T);
+	const size_t blocks = (words + kNzBlockWords - 1) / kNzBlockWords;
+	H.table = host_table; H.words = words; H.n_slices = slices_for(blocks);
+	H.zeroed.assign((size_t)H.n_slices, 0);
+	H.next = 0; H.cancel = false; H.active = true;
+	ReadbackHost* h = &H;
+	H.pool.submit([h, blocks](int) {
+		for (;;) {
+			if (h->cancel.load()) break;
+			const int s = h->next.fetch_add(1);
+			if (s >= h->n_slices) break;
+			const size_t w0 = blocks * (size_t)s / (size_t)h->n_slices * kNzBlockWords;
+			size_t w1 = blocks * (size_t)(s + 1) / (size_t)h->n_slices * kNzBlockWords;
+			if (w1 > h->words) w1 = h->words;
+			readback_expand_slice(h->table, w0, w1, nullptr, 0, 0, false);
+			h->zeroed[(size_t)s] = 1;
+		}
+	});
+}
+
+// Stops a zero-fill that is still running ahead (error paths: nobody may write the caller's table after the call has returned).
+void readback_cancel(Readback& rb) {
+	if (rb.host) settle_prezero(*static_cast<ReadbackHost*>(rb.host));
 }
 
 int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsigned int* host_table, cudaStream_t st, int host_threads) {
@@ -98,9 +236,11 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 	static const bool portable = getenv("VOXB200_READBACK_SSE2") != nullptr;      // tests: the path of CPUs without AVX-512
 	const auto t0 = std::chrono::steady_clock::now();
 	auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
-	const bool eligible = words != 0 && (words & 15u) == 0 && words <= 0xffffffffull && (reinterpret_cast<uintptr_t>(host_table) & 63u) == 0 &&
-	                      (reinterpret_cast<uintptr_t>(d_table) & 15u) == 0;
-	if (!eligible || force == 1 || (bytes < kSparseMinBytes && force != 2)) return dense_copy(rb, d_table, words, host_table, st);
+	ReadbackHost& H = host_of(rb);
+	const bool prezero = H.active && H.table == host_table && H.words == words;
+	if (H.active && !prezero) settle_prezero(H);          // somebody else's table: just stop it
+	auto dense = [&]() -> int { settle_prezero(H); return dense_copy(rb, d_table, words, host_table, st); };
+	if (!sparse_eligible(d_table, words, host_table)) return dense();
 	const size_t blocks = (words + kNzBlockWords - 1) / kNzBlockWords;
 	if (blocks + 1 > rb.blocks_cap) {
 		size_t a = 0, b = 0;
@@ -120,7 +260,7 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 	const unsigned long long nnz = rb.h_offsets[blocks];
 	const double t_count = since();
 	// 8 bytes per pair against 4 bytes per word, plus the host's own pass over the table (~1/3 of the dense copy's time)
-	if (force != 2 && nnz * 8ull > bytes / 3) return dense_copy(rb, d_table, words, host_table, st);
+	if (force != 2 && nnz * 8ull > bytes / 3) return dense();
 	if (nnz > rb.pairs_cap) {
 		const size_t want = (size_t)(nnz + nnz / 4 + 1024);
 		uint2* p = reinterpret_cast<uint2*>(rb.d_pairs);
@@ -134,8 +274,7 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 	}
 	// pass 2: the pairs, then slice by slice over the link
 	RB_CU(launch_nz_write(d_table, words, rb.d_offsets, rb.d_pairs, st));
-	static const int want_slices = [] { const char* e = getenv("VOXB200_READBACK_SLICES"); const int v = e ? atoi(e) : 64; return v < 1 ? 1 : v > kMaxSlices ? kMaxSlices : v; }();
-	const int n_slices = (int)(blocks < (size_t)want_slices ? blocks : (size_t)want_slices);
+	const int n_slices = slices_for(blocks);
 	std::vector<size_t> b0(n_slices + 1);
 	for (int s = 0; s <= n_slices; s++) b0[s] = blocks * (size_t)s / (size_t)n_slices;
 	const uint2* d_pairs = reinterpret_cast<const uint2*>(rb.d_pairs);
@@ -146,30 +285,37 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 		RB_CU(cudaEventRecord(rb.ev[s], st));
 	}
 	const double t_enqueued = since();
+	// the zero-fill that ran ahead stops here: slices it finished only need their non-zero lines, the others the full pass
+	settle_prezero(H);
+	int n_zeroed = 0;
+	if (prezero) for (int s = 0; s < n_slices; s++) n_zeroed += H.zeroed[(size_t)s];
+	const double t_settled = since();
 	int dev = -1;
 	cudaGetDevice(&dev);
 	std::atomic<int> next{0};
 	std::atomic<int> cuda_error{0};
-	auto work = [&] {
+	const int T = host_threads > 0 ? host_threads : readback_default_threads();
+	H.pool.resize(T);
+	const unsigned long long* off = rb.h_offsets;
+	cudaEvent_t* ev = rb.ev;
+	const unsigned char* zeroed = prezero ? H.zeroed.data() : nullptr;
+	H.pool.submit([&, off, ev, zeroed](int) {
 		if (dev >= 0) cudaSetDevice(dev);
 		for (;;) {
 			const int s = next.fetch_add(1);
 			if (s >= n_slices) break;
-			const cudaError_t e = cudaEventSynchronize(rb.ev[s]);
+			const cudaError_t e = cudaEventSynchronize(ev[s]);
 			if (e != cudaSuccess) { cuda_error = (int)e; break; }
 			const size_t w0 = b0[s] * kNzBlockWords, w1 = b0[s + 1] * kNzBlockWords < words ? b0[s + 1] * kNzBlockWords : words;
-			(portable ? readback_expand_slice_sse2 : readback_expand_slice)(host_table, w0, w1, h_pairs, (size_t)rb.h_offsets[b0[s]], (size_t)rb.h_offsets[b0[s + 1]]);
+			const bool lines_only = zeroed && zeroed[s];
+			(portable ? readback_expand_slice_sse2 : readback_expand_slice)(host_table, w0, w1, h_pairs, (size_t)off[b0[s]], (size_t)off[b0[s + 1]], lines_only);
 		}
-	};
-	const int T = host_threads > 0 ? host_threads : readback_default_threads();
-	std::vector<std::thread> pool;
-	for (int t = 1; t < T && t < n_slices; t++) pool.emplace_back(work);
-	work();
-	for (auto& t : pool) t.join();
+	});
+	H.pool.wait();
 	const double t_expanded = since();
 	RB_CU(cudaStreamSynchronize(st));
-	if (debug) fprintf(stderr, "[voxb200 readback] %zu MB, %llu non-zero words, %d threads: count+sync %.3f ms, pairs enqueued %.3f, expanded %.3f\n",
-	                   bytes >> 20, nnz, T, t_count, t_enqueued, t_expanded);
+	if (debug) fprintf(stderr, "[voxb200 readback] %zu MB, %llu non-zero words, %d threads: count+sync %.3f ms, pairs enqueued %.3f, zero-fill ahead settled %.3f (%d of %d slices), expanded %.3f\n",
+	                   bytes >> 20, nnz, T, t_count, t_enqueued, t_settled, n_zeroed, n_slices, t_expanded);
 	if (cuda_error) return abi_fail_cuda((cudaError_t)cuda_error.load(), "readback: cudaEventSynchronize");
 	rb.last_mode = 1; rb.last_nonzero = nnz;
 	return VOXB200_OK;

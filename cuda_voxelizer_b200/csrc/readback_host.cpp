@@ -24,6 +24,7 @@ inline __m128i put32(__m128i v, unsigned int k, unsigned int val) {          // 
 	return _mm_or_si128(v, x);
 }
 
+template <bool LINES_ONLY>
 void expand_sse2(unsigned int* table, size_t w0, size_t w1, const Pair* pairs, size_t p0, size_t p1) {
 	const __m128i z = _mm_setzero_si128();
 	size_t line = w0 >> 4;
@@ -31,6 +32,7 @@ void expand_sse2(unsigned int* table, size_t w0, size_t w1, const Pair* pairs, s
 	size_t p = p0;
 	while (line < end) {
 		const size_t next = p < p1 ? (size_t)(pairs[p].x >> 4) : end;
+		if (LINES_ONLY) line = next;
 		for (; line < next; line++) {
 			__m128i* q = reinterpret_cast<__m128i*>(table + (line << 4));
 			_mm_stream_si128(q, z); _mm_stream_si128(q + 1, z); _mm_stream_si128(q + 2, z); _mm_stream_si128(q + 3, z);
@@ -54,6 +56,7 @@ void expand_sse2(unsigned int* table, size_t w0, size_t w1, const Pair* pairs, s
 	_mm_sfence();
 }
 
+template <bool LINES_ONLY>
 __attribute__((target("avx512f"))) void expand_avx512(unsigned int* table, size_t w0, size_t w1, const Pair* pairs, size_t p0, size_t p1) {
 	const __m512i z = _mm512_setzero_si512();
 	size_t line = w0 >> 4;
@@ -61,6 +64,7 @@ __attribute__((target("avx512f"))) void expand_avx512(unsigned int* table, size_
 	size_t p = p0;
 	while (line < end) {
 		const size_t next = p < p1 ? (size_t)(pairs[p].x >> 4) : end;
+		if (LINES_ONLY) line = next;
 		for (; line < next; line++) _mm512_stream_si512(reinterpret_cast<__m512i*>(table + (line << 4)), z);
 		if (line >= end) break;
 		__m512i v = z;
@@ -77,14 +81,17 @@ __attribute__((target("avx512f"))) void expand_avx512(unsigned int* table, size_
 }  // namespace
 
 // table: 64-byte aligned; w0, w1: multiples of 16 words; pairs[p0..p1): exactly the pairs with w0 <= x < w1, ascending.
-void readback_expand_slice(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1) {
+// lines_only: the words are already zero — write just the lines that hold a pair.
+void readback_expand_slice(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1, bool lines_only) {
 	static const bool avx512 = __builtin_cpu_supports("avx512f");
-	if (avx512) expand_avx512(table, w0, w1, static_cast<const Pair*>(pairs), p0, p1);
-	else expand_sse2(table, w0, w1, static_cast<const Pair*>(pairs), p0, p1);
+	const Pair* pp = static_cast<const Pair*>(pairs);
+	if (avx512) { if (lines_only) expand_avx512<true>(table, w0, w1, pp, p0, p1); else expand_avx512<false>(table, w0, w1, pp, p0, p1); }
+	else { if (lines_only) expand_sse2<true>(table, w0, w1, pp, p0, p1); else expand_sse2<false>(table, w0, w1, pp, p0, p1); }
 }
 // (tests) the portable path, whatever the CPU
-void readback_expand_slice_sse2(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1) {
-	expand_sse2(table, w0, w1, static_cast<const Pair*>(pairs), p0, p1);
+void readback_expand_slice_sse2(unsigned int* table, size_t w0, size_t w1, const void* pairs, size_t p0, size_t p1, bool lines_only) {
+	const Pair* pp = static_cast<const Pair*>(pairs);
+	if (lines_only) expand_sse2<true>(table, w0, w1, pp, p0, p1); else expand_sse2<false>(table, w0, w1, pp, p0, p1);
 }
 
 }  // namespace voxb

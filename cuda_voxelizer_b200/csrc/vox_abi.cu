@@ -640,6 +640,8 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 		hp.table_bytes = table_bytes;
 	}
 	cudaStream_t st = hp.stream;
+	ReadbackGuard guard{hp.rb};
+	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0);      // surface tables are sparse: zero-fill the host table meanwhile
 	CU(cudaEventRecord(hp.ev[0], st));
 	rc = h2d(hp, hp.d_tris, host_tris9, tris_bytes, st);
 	if (rc) return rc;
@@ -680,6 +682,8 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 	if (!tiles && (rc = grow(&hp.d_tris, &hp.tris_bytes, n_faces * 9 * sizeof(float) + 16))) return rc;
 	if ((rc = grow(&hp.d_table, &hp.table_bytes, table_bytes))) return rc;
 	cudaStream_t st = hp.stream;
+	ReadbackGuard guard{hp.rb};
+	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0);      // surface tables are sparse: zero-fill the host table meanwhile
 	CU(cudaEventRecord(hp.ev[0], st));
 	rc = h2d(hp, hp.d_verts, host_verts, n_verts * 3 * sizeof(float), st);
 	if (!rc) rc = h2d(hp, hp.d_faces, host_faces, n_faces * 3 * sizeof(int), st);

@@ -181,11 +181,16 @@ struct Readback {
 	void* d_pairs = nullptr; size_t pairs_cap = 0;                          // pairs
 	void* h_pairs = nullptr; size_t h_pairs_cap = 0;                        // pinned
 	cudaEvent_t* ev = nullptr; int n_ev = 0;
+	void* host = nullptr;                   // host threads + the zero-fill that runs ahead (readback.cu)
 	// what the last call did
 	int last_mode = 0;                      // 0 dense copy, 1 sparse
 	unsigned long long last_nonzero = 0;    // non-zero words (sparse mode)
 };
 int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsigned int* host_table, cudaStream_t st, int host_threads);
+// Optional, before the upload of a call whose table is expected to be sparse: host threads start zero-filling host_table now.
+void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads);
+void readback_cancel(Readback& rb);          // every exit of a call that started one (idempotent)
+struct ReadbackGuard { Readback& rb; ~ReadbackGuard() { readback_cancel(rb); } };
 void readback_free(Readback& rb);
 int readback_default_threads();
 cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);

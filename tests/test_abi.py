@@ -194,17 +194,20 @@ def test_readback_host_expansion_rebuilds_the_table(vb):
         idx = np.flatnonzero(rng.random(words) < density)
         want[idx] = rng.integers(1, 2**32, len(idx), dtype=np.uint64).astype(np.uint32)
         pairs = np.stack([idx.astype(np.uint32), want[idx]], axis=1).copy()
-        for sym in ("_ZN4voxb21readback_expand_sliceEPjmmPKvmm", "_ZN4voxb26readback_expand_slice_sse2EPjmmPKvmm"):
+        for sym in ("_ZN4voxb21readback_expand_sliceEPjmmPKvmmb", "_ZN4voxb26readback_expand_slice_sse2EPjmmPKvmmb"):
             fn = getattr(L, sym)
-            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]
+            fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_bool]
             fn.restype = None
             raw = np.full(words + 32, 0xDEADBEEF, np.uint32)
             off = (-(raw.ctypes.data // 4)) % 16
             table = raw[off:off + words]
-            # two slices, cut on a line boundary in the middle of the pairs
+            # two slices, cut on a line boundary in the middle of the pairs: the first gets the full pass, the second is zero-filled
+            # ahead (no pairs) and then only gets its non-zero lines
             cut = 16 * 2311
             pc = int(np.searchsorted(idx, cut))
-            fn(table.ctypes.data, 0, cut, pairs.ctypes.data, 0, pc)
-            fn(table.ctypes.data, cut, words, pairs.ctypes.data, pc, len(idx))
+            fn(table.ctypes.data, 0, cut, pairs.ctypes.data, 0, pc, False)
+            fn(table.ctypes.data, cut, words, None, 0, 0, False)
+            assert not table[cut:].any()
+            fn(table.ctypes.data, cut, words, pairs.ctypes.data, pc, len(idx), True)
             assert np.array_equal(table, want), (density, sym)
             assert raw[off + words] == 0xDEADBEEF and (off == 0 or raw[off - 1] == 0xDEADBEEF)
