@@ -170,6 +170,19 @@ def set_readback_mode(mode):
     check(_lib.lib().voxb200_set_readback_mode({"auto": 0, "dense": 1, "sparse": 2}[mode]))
 
 
+def binvox_rle(d_table, gridsize, stream=None):
+    """voxb200_binvox_rle: the binvox payload (numpy uint8) of a linear CUDA table, run-length encoded on the device."""
+    ptr, n = C.c_void_p(), C.c_size_t()
+    check(_lib.lib().voxb200_binvox_rle(C.c_void_p(d_table.data_ptr()), int(gridsize), C.byref(ptr), C.byref(n), _stream_ptr(stream)))
+    out = np.empty(n.value, np.uint8)
+    try:
+        if n.value:
+            check(_lib.lib().voxb200_memcpy_d2h(C.c_void_p(out.ctypes.data), ptr, n.value, None))
+    finally:
+        _lib.lib().voxb200_free(ptr)
+    return out
+
+
 def set_host_threads(n):
     check(_lib.lib().voxb200_set_host_threads(int(n)))
 

@@ -38,6 +38,7 @@ struct VoxelList {
 // the same bytes, produced from the voxel list instead of G^3 checkVoxel() calls.
 void write_binary(const void* data, size_t bytes, const std::string& base_filename);                       // -o morton
 void write_binvox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);             // -o binvox
+void write_binvox_payload(const unsigned char* payload, size_t bytes, const voxinfo& info, const std::string& base_filename);   // -o binvox, G % 256 == 0
 void write_obj_pointcloud(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);     // -o obj_points
 void write_obj_cubes(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);          // -o obj
 void write_vox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename);                // -o vox

@@ -200,10 +200,25 @@ int main(int argc, char* argv[]) {
 	VoxelList voxels;
 	voxels.gridsize = opt.gridsize;
 	const double t_rb = now_ms();
+	// -o binvox on grids the device encoder covers: the run-length encoded payload is built on the GPU and is all that crosses PCIe
+	std::vector<unsigned char> rle;
+	const bool device_rle = opt.format == Format::binvox && opt.gridsize >= 256 && opt.gridsize % 256 == 0 && opt.gridsize <= 4096;
 	if (morton) {
 		vtable.resize(vtable_size / 4);
 		rc = voxb200_memcpy_d2h(vtable.data(), d_table, vtable_size, nullptr);
 		if (rc) die_abi("voxb200_memcpy_d2h", rc);
+	} else if (device_rle) {
+		unsigned char* d_rle = nullptr;
+		size_t n_rle = 0;
+		rc = voxb200_binvox_rle(d_table, opt.gridsize, &d_rle, &n_rle, nullptr);
+		if (rc) die_abi("voxb200_binvox_rle", rc);
+		rle.resize(n_rle);
+		if (n_rle) {
+			rc = voxb200_memcpy_d2h(rle.data(), d_rle, n_rle, nullptr);
+			if (rc) die_abi("voxb200_memcpy_d2h", rc);
+		}
+		voxb200_free(d_rle);
+		printf("[Voxel Grid] binvox payload: %zu bytes (run-length encoded on the GPU) \n", n_rle);
 	} else {
 		uint64_t* d_idx = nullptr;
 		size_t n_set = 0;
@@ -225,7 +240,7 @@ int main(int argc, char* argv[]) {
 	const double t_out = now_ms();
 	switch (opt.format) {
 		case Format::morton: write_binary(vtable.data(), vtable_size, opt.filename); break;
-		case Format::binvox: write_binvox(voxels, info, opt.filename); break;
+		case Format::binvox: if (device_rle) write_binvox_payload(rle.data(), rle.size(), info, opt.filename); else write_binvox(voxels, info, opt.filename); break;
 		case Format::obj_points: write_obj_pointcloud(voxels, info, opt.filename); break;
 		case Format::obj_cubes: write_obj_cubes(voxels, info, opt.filename); break;
 		case Format::vox: write_vox(voxels, info, opt.filename); break;

@@ -57,16 +57,29 @@ static std::vector<uint64_t> traversal_keys(const VoxelList& vox, Axis a, Axis b
 	return keys;
 }
 
-void write_binvox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
-	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + ".binvox";
-	fprintf(stdout, "[I/O] Writing data in binvox format to %s \n", name.c_str());
-	std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
+static void binvox_header(std::ofstream& out, const voxinfo& info) {          // util_io.cpp:210-216
 	const float sx = info.bbox.max.x - info.bbox.min.x, sy = info.bbox.max.y - info.bbox.min.y, sz = info.bbox.max.z - info.bbox.min.z;
 	out << "#binvox 1" << std::endl;
 	out << "dim " << info.gridsize.x << " " << info.gridsize.y << " " << info.gridsize.z << std::endl;
 	out << "translate " << info.bbox.min.x << " " << info.bbox.min.y << " " << info.bbox.min.z << std::endl;
 	out << "scale " << std::max(std::max(sx, sy), sz) << std::endl;
 	out << "data" << std::endl;
+}
+
+// The payload was run-length encoded on the device (voxb200_binvox_rle): header + bytes.
+void write_binvox_payload(const unsigned char* payload, size_t bytes, const voxinfo& info, const std::string& base_filename) {
+	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + ".binvox";
+	fprintf(stdout, "[I/O] Writing data in binvox format to %s \n", name.c_str());
+	std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
+	binvox_header(out, info);
+	out.write(reinterpret_cast<const char*>(payload), (std::streamsize)bytes);
+}
+
+void write_binvox(const VoxelList& vox, const voxinfo& info, const std::string& base_filename) {
+	const std::string name = base_filename + "_" + std::to_string(info.gridsize.x) + ".binvox";
+	fprintf(stdout, "[I/O] Writing data in binvox format to %s \n", name.c_str());
+	std::ofstream out(name.c_str(), std::ios::out | std::ios::binary);
+	binvox_header(out, info);
 	// (value, count <= 255) pairs over the voxels visited x-major, then z, then y (util_io.cpp:219-240): a run of L equal
 	// voxels comes out as (v,255) pairs and a remainder, exactly what the reference's counter produces
 	const uint64_t G = vox.gridsize, total = G * G * G;

@@ -272,6 +272,13 @@ int voxb200_mesh_destroy(voxb200_mesh* mesh);
  * voxel, 0 for a whole table).  *d_indices is allocated here (voxb200_free it).  Synchronises `stream`.
  */
 int voxb200_extract_voxels(const unsigned int* d_table, size_t table_words, uint64_t first_voxel, uint64_t** d_indices, size_t* count, void* stream);
+/*
+ * Table consumer for the binvox writer (util_io.cpp:202-246): the run-length encoded payload — (value, count <= 255) byte pairs
+ * over the voxels visited x-major, then z, then y — of a whole LINEAR table, built on the device, byte-identical to what the
+ * reference's G^3 checkVoxel loop writes after its ASCII header.  gridsize: a multiple of 256, at most 4096 (smaller grids: walk
+ * the voxel list).  *d_bytes is allocated here (voxb200_free it), *n_bytes its size.  Synchronises `stream`.
+ */
+int voxb200_binvox_rle(const unsigned int* d_table, unsigned int gridsize, unsigned char** d_bytes, size_t* n_bytes, void* stream);
 
 /* ---- introspection ---------------------------------------------------------------------------- */
 /* Kernels launched by this library since the last reset (the bench's "gpu_launches"). */

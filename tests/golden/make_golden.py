@@ -90,5 +90,32 @@ def make_writer_goldens(verts, faces):
     shutil.rmtree(tmp)
 
 
+def make_binvox_goldens():
+    """Size + FNV-1a-64 of the reference writer's binvox FILES at grid sizes the device encoder covers (voxb200_binvox_rle)."""
+    import shutil
+    import tempfile
+    import cases
+    v, f = cases.mesh("bunny")
+    out = {}
+    tmp = tempfile.mkdtemp()
+    for g, solid in ((256, 0), (256, 1), (512, 0)):
+        mn, mx, unit = oracle.ref_voxinfo(v, g, len(f))
+        table = oracle.ref_voxelize(v, f, g, solid=bool(solid), threads=1)
+        base = os.path.join(tmp, "bunny.OBJ")
+        oracle.ref_write("binvox", table, g, mn, mx, len(f), base)
+        data = np.fromfile(base + "_%d.binvox" % g, np.uint8)
+        header_end = data.tobytes().index(b"data\n") + 5
+        key = "bunny|%d|%s" % (g, "solid" if solid else "surface")
+        out[key] = {"bytes": int(len(data)), "header_bytes": int(header_end), "fnv1a64": "%016x" % oracle.fnv1a64(data),
+                    "payload_fnv1a64": "%016x" % oracle.fnv1a64(data[header_end:])}
+        print("binvox golden", key, out[key])
+    json.dump(out, open(os.path.join(HERE, "io", "binvox_large.json"), "w"), indent=1, sort_keys=True)
+    shutil.rmtree(tmp)
+
+
 if __name__ == "__main__":
-    main()
+    if "--binvox" in sys.argv:
+        make_binvox_goldens()
+    else:
+        main()
+        make_binvox_goldens()
