@@ -129,3 +129,131 @@ def test_parallel_obj_loader_matches_the_line_by_line_parser(work, tmp_path):
     v, f = _dump(work["obj"], str(tmp_path / "bunny.bin"))
     bv, bf = cases.mesh("bunny")
     assert np.array_equal(v, bv) and np.array_equal(f, bf)
+
+
+def _tess_quad(v, q):
+    """trimesh2's tess() rule for a quad: split along the shorter diagonal."""
+    d02 = np.float32(((v[q[0]] - v[q[2]]) ** 2).sum(dtype=np.float32))
+    d13 = np.float32(((v[q[1]] - v[q[3]]) ** 2).sum(dtype=np.float32))
+    i = 0 if d02 < d13 else 1
+    return [[q[i], q[(i + 1) % 4], q[(i + 2) % 4]], [q[i], q[(i + 2) % 4], q[(i + 3) % 4]]]
+
+
+def test_quads_are_split_along_the_shorter_diagonal(tmp_path):
+    """OBJ and PLY polygons: triangles as they are, quads along the shorter diagonal, larger polygons as a fan (trimesh2 tess())."""
+    v = np.array([[0, 0, 0], [4, 0, 0], [4, 1, 0], [0, 1, 0],          # d02 == d13: corner 1
+                  [0, 0, 1], [1, 0, 1], [5, 3, 1], [0, 1, 1],          # d13 shorter: corner 1
+                  [0, 0, 2], [1, 0, 2], [1, 1, 2], [-5, 4, 2],         # d02 shorter: corner 0
+                  [9, 9, 9], [8, 9, 9], [8, 8, 9], [9, 7, 9], [9.5, 8, 9]], np.float32)
+    polys = [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9, 10, 11], [12, 13, 14, 15, 16], [0, 4, 8]]
+    want = []
+    for p in polys:
+        if len(p) == 4:
+            want += _tess_quad(v, p)
+        else:
+            want += [[p[0], p[k], p[k + 1]] for k in range(1, len(p) - 1)]
+    want = np.array(want, np.int32)
+    obj = tmp_path / "quads.obj"
+    with open(obj, "w") as fh:
+        for p in v:
+            fh.write("v %.9g %.9g %.9g\n" % tuple(p))
+        for p in polys:
+            fh.write("f " + " ".join(str(i + 1) for i in p) + "\n")
+    for env in ({"VOXCLI_SERIAL_LOADER": "1"}, {}):
+        gv, gf = _dump(str(obj), str(tmp_path / "q.bin"), env)
+        assert np.array_equal(gv, v) and np.array_equal(gf, want), env
+    ply = tmp_path / "quads.ply"
+    with open(ply, "w") as fh:
+        fh.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nelement face %d\nproperty list uchar int vertex_indices\nend_header\n" % (len(v), len(polys)))
+        for p in v:
+            fh.write("%.9g %.9g %.9g\n" % tuple(p))
+        for p in polys:
+            fh.write("%d %s\n" % (len(p), " ".join(map(str, p))))
+    gv, gf = _dump(str(ply), str(tmp_path / "q.bin"))
+    assert np.array_equal(gv, v) and np.array_equal(gf, want)
+
+
+def _write_ply(path, v, faces, fmt, vertex_layout="xyz", strips=None, index_type="int", count_type="uchar"):
+    """faces: list of index lists.  vertex_layout: 'xyz' | 'nxyz' (a float property in front and a uchar behind) | 'double'."""
+    end = {"binary_little_endian": "<", "binary_big_endian": ">", "ascii": "<"}[fmt]
+    vt = "double" if vertex_layout == "double" else "float"
+    props = []
+    if vertex_layout == "nxyz":
+        props.append("property float confidence")
+    props += ["property %s x" % vt, "property %s y" % vt, "property %s z" % vt]
+    if vertex_layout == "nxyz":
+        props.append("property uchar red")
+    head = "ply\nformat %s 1.0\ncomment made by the tests\nelement vertex %d\n%s\n" % (fmt, len(v), "\n".join(props))
+    if faces is not None:
+        head += "element face %d\nproperty list %s %s vertex_indices\n" % (len(faces), count_type, index_type)
+    if strips is not None:
+        head += "element tristrips %d\nproperty list int int vertex_indices\n" % len(strips)
+    head += "end_header\n"
+    np_t = {"int": "i4", "uint": "u4", "short": "i2", "uchar": "u1", "int32": "i4"}
+    with open(path, "wb") as fh:
+        fh.write(head.encode())
+        if fmt == "ascii":
+            for p in v:
+                row = ["%.9g" % c for c in p]
+                if vertex_layout == "nxyz":
+                    row = ["0.5"] + row + ["200"]
+                fh.write((" ".join(row) + "\n").encode())
+            for f in faces or []:
+                fh.write(("%d %s\n" % (len(f), " ".join(map(str, f)))).encode())
+            for s in strips or []:
+                fh.write(("%d %s\n" % (len(s), " ".join(map(str, s)))).encode())
+        else:
+            for p in v:
+                if vertex_layout == "nxyz":
+                    fh.write(np.array([0.5], end + "f4").tobytes())
+                fh.write(np.asarray(p, end + ("f8" if vt == "double" else "f4")).tobytes())
+                if vertex_layout == "nxyz":
+                    fh.write(b"\xc8")
+            for f in faces or []:
+                fh.write(np.array([len(f)], end + np_t[count_type]).tobytes() + np.asarray(f, end + np_t[index_type]).tobytes())
+            for s in strips or []:
+                fh.write(np.array([len(s)], end + "i4").tobytes() + np.asarray(s, end + "i4").tobytes())
+
+
+def test_ply_variants_load_the_same_mesh(work, tmp_path):
+    """ASCII / binary little- and big-endian PLY, extra vertex properties around x y z, double coordinates, other index types,
+    files big enough to be parsed by several threads, at several thread counts: all give the bunny's arrays."""
+    bv, bf = cases.mesh("bunny")
+    reps = 12                                                   # > 1 MB of ASCII: the parallel paths really run
+    v = np.concatenate([bv + np.float32(10 * k) for k in range(reps)])
+    f = np.concatenate([bf + len(bv) * k for k in range(reps)]).astype(np.int32)
+    faces = [list(t) for t in f]
+    n = 0
+    for fmt in ("ascii", "binary_little_endian", "binary_big_endian"):
+        for layout in ("xyz", "nxyz", "double"):
+            path = str(tmp_path / ("m%d.ply" % n))
+            n += 1
+            _write_ply(path, v, faces, fmt, layout)
+            for threads in ("1", "5"):
+                gv, gf = _dump(path, str(tmp_path / "p.bin"), {"VOXCLI_LOADER_THREADS": threads})
+                assert np.array_equal(gv, v) and np.array_equal(gf, f), (fmt, layout, threads)
+    path = str(tmp_path / "short.ply")
+    _write_ply(path, bv, [list(t) for t in bf], "binary_little_endian", index_type="short", count_type="int")
+    gv, gf = _dump(path, str(tmp_path / "p.bin"))
+    assert np.array_equal(gv, bv) and np.array_equal(gf, bf)
+
+
+def test_ply_triangle_strips(tmp_path):
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0], [0, 2, 0], [1, 2, 0], [5, 5, 5], [6, 5, 5], [5, 6, 5]], np.float32)
+    strips = [[0, 1, 2, 3, 4, 5, -1, 6, 7, 8]]
+    want = np.array([[0, 1, 2], [2, 1, 3], [2, 3, 4], [4, 3, 5], [6, 7, 8]], np.int32)     # every second triangle flipped back
+    for fmt in ("ascii", "binary_little_endian"):
+        path = str(tmp_path / ("s_%s.ply" % fmt))
+        _write_ply(path, v, None, fmt, strips=strips)
+        gv, gf = _dump(path, str(tmp_path / "p.bin"))
+        assert np.array_equal(gv, v) and np.array_equal(gf, want), fmt
+
+
+def test_truncated_ply_is_an_error(tmp_path):
+    bv, bf = cases.mesh("bunny")
+    path = str(tmp_path / "t.ply")
+    _write_ply(path, bv, [list(t) for t in bf], "binary_little_endian")
+    raw = open(path, "rb").read()
+    open(path, "wb").write(raw[:-100])
+    r = subprocess.run([CLI, "-f", path, "-s", "64", "--dump-mesh", str(tmp_path / "x.bin")], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and "ends inside element" in r.stdout + r.stderr
