@@ -14,27 +14,53 @@ from . import api
 
 
 def owned_region(gridsize, morton, rank=None, world=None):
-    """(Region, bytes) of this rank.  Regions of all ranks tile the table in rank order and have equal size."""
+    """(Region, bytes) of this rank.  Regions of all ranks tile the table in rank order; z-slabs differ in size when the world
+    size does not divide the grid (voxb200_partition cuts z at floor(G * part / n))."""
     rank = dist.get_rank() if rank is None else rank
     world = dist.get_world_size() if world is None else world
     return api.partition(gridsize, morton, rank, world)
 
 
-def gather_table(local_table, group=None):
-    """All-gather the per-rank regions into the full table on every rank (equal-sized regions)."""
+def _region_sizes(local_table, group):
+    """numel of every rank's region (they differ when the world size does not divide the grid)."""
     world = dist.get_world_size(group)
-    out = torch.empty(world * local_table.numel(), dtype=local_table.dtype, device=local_table.device)
-    dist.all_gather_into_tensor(out, local_table.contiguous(), group=group)
-    return out
+    mine = torch.tensor([local_table.numel()], dtype=torch.int64, device=local_table.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=local_table.device)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
+    return [int(x) for x in sizes.tolist()]
+
+
+def gather_table(local_table, group=None):
+    """All-gather the per-rank regions into the full table on every rank.  Equal regions: one all_gather_into_tensor; unequal
+    ones are padded to the largest for the collective and cut back afterwards."""
+    world = dist.get_world_size(group)
+    sizes = _region_sizes(local_table, group)
+    local_table = local_table.contiguous()
+    if len(set(sizes)) == 1:
+        out = torch.empty(world * local_table.numel(), dtype=local_table.dtype, device=local_table.device)
+        dist.all_gather_into_tensor(out, local_table, group=group)
+        return out
+    big = max(sizes)
+    padded = torch.zeros(big, dtype=local_table.dtype, device=local_table.device)
+    padded[: local_table.numel()] = local_table
+    out = torch.empty(world * big, dtype=local_table.dtype, device=local_table.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * big: r * big + sizes[r]] for r in range(world)])
 
 
 def gather_table_to(local_table, dst=0, group=None):
-    """Gather the regions on rank ``dst`` only (returns None elsewhere)."""
+    """Gather the regions on rank ``dst`` only (returns None elsewhere); regions may differ in size."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    bufs = [torch.empty_like(local_table) for _ in range(world)] if rank == dst else None
-    dist.gather(local_table.contiguous(), bufs, dst=dst, group=group)
-    return torch.cat(bufs) if rank == dst else None
+    sizes = _region_sizes(local_table, group)
+    big = max(sizes)
+    send = local_table.contiguous()
+    if send.numel() != big:
+        send = torch.zeros(big, dtype=local_table.dtype, device=local_table.device)
+        send[: local_table.numel()] = local_table
+    bufs = [torch.empty(big, dtype=local_table.dtype, device=local_table.device) for _ in range(world)] if rank == dst else None
+    dist.gather(send, bufs, dst=dst, group=group)
+    return torch.cat([bufs[r][: sizes[r]] for r in range(world)]) if rank == dst else None
 
 
 def exchange_routed(send, send_counts, group=None):
@@ -84,7 +110,23 @@ class ShardedHostVoxelizer:
         d_chunk.copy_(host_chunk, non_blocking=True)
         g_local = self._copy(self.grid)
         g_local.n_triangles = n_local
-        counts = api.route_triangles_multi(g_local, d_chunk, self.regions, self.send, solid=self.solid, morton=self.morton, stream=st)
+        # A triangle is written once per region it overlaps, so the routed soup can outgrow the 2x buffer.  That shows on one rank
+        # only; ranks must not part ways in front of the all-to-all, so they agree on it first and grow together (n_local * world
+        # triangles always fit).
+        try:
+            counts = api.route_triangles_multi(g_local, d_chunk, self.regions, self.send, solid=self.solid, morton=self.morton, stream=st)
+            overflow = 0
+        except api.VoxError as e:
+            if "exceed the output capacity" not in str(e):
+                raise
+            counts, overflow = None, 1
+        flag = torch.tensor([overflow], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+        if int(flag.item()):
+            need = self.world * host_chunk.numel() + 9 * 1024
+            if self.send.numel() < need:
+                self.send = torch.empty(need, dtype=torch.float32, device="cuda")
+            counts = api.route_triangles_multi(g_local, d_chunk, self.regions, self.send, solid=self.solid, morton=self.morton, stream=st)
         recv, recv_counts = exchange_routed(self.send, counts)
         g_mine = self._copy(self.grid)
         g_mine.n_triangles = sum(recv_counts)

@@ -1,4 +1,4 @@
-"""CPU suite: the N>1 host logic on the gloo backend, world_size 2 and 4.  Each rank derives its region through
+"""CPU suite: the N>1 host logic on the gloo backend, world_size 2, 3 (slabs of unequal size: 21 / 21 / 22 layers of 64) and 4.  Each rank derives its region through
 the product's partition logic, fills it with the ORACLE restricted to that region (the checker standing in
 for the GPU kernel, which cannot run here), and the product's gather must reproduce the oracle's full table."""
 import os
@@ -69,7 +69,7 @@ def _worker(rank, world, port, solid, result_path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 3, 4])
 @pytest.mark.parametrize("solid", [False, True])
 def test_slab_sharding_and_gather_on_gloo(tmp_path, world, solid):
     result = str(tmp_path / "result.txt")
