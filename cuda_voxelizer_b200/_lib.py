@@ -23,7 +23,7 @@ EXPORTS = [
     "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release", "voxb200_sort_triangles",
     "voxb200_reference_table_bytes", "voxb200_mesh_create", "voxb200_mesh_create_indexed", "voxb200_mesh_update", "voxb200_mesh_update_indexed",
     "voxb200_mesh_voxelize", "voxb200_mesh_info", "voxb200_mesh_destroy", "voxb200_mesh_counters",
-    "voxb200_voxelize_host_multi", "voxb200_gather_slabs", "voxb200_host_alloc", "voxb200_host_free", "voxb200_download_table", "voxb200_binvox_rle", "voxb200_last_readback", "voxb200_set_readback_mode", "voxb200_set_host_threads",
+    "voxb200_voxelize_host_multi", "voxb200_gather_slabs", "voxb200_host_alloc", "voxb200_host_free", "voxb200_download_table", "voxb200_binvox_rle", "voxb200_last_readback", "voxb200_set_readback_mode", "voxb200_set_host_threads", "voxb200_selftest_host_pool",
 ]
 
 

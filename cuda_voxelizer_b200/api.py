@@ -125,7 +125,10 @@ class DeviceBuffer:
 
     def close(self):
         if self.ptr:
-            _lib.lib().voxb200_free(C.c_void_p(self.ptr))
+            try:
+                _lib.lib().voxb200_free(C.c_void_p(self.ptr))
+            except TypeError:          # interpreter shutdown: the module globals are gone, the process is about to release the memory
+                pass
             self.ptr = 0
 
     __del__ = close

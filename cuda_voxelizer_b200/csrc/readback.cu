@@ -110,8 +110,7 @@ class HostPool {
 	unsigned long long generation_ = 0;
 	int running_ = 0;
 	bool stop_ = false;
-	void loop(int w) {
-		unsigned long long seen = 0;
+	void loop(int w, unsigned long long seen) {               // seen: the generation at the thread's creation (it must not run an older job)
 		for (;;) {
 			std::function<void(int)> job;
 			{
@@ -134,7 +133,8 @@ public:
 		if (n == size()) return;
 		shutdown();
 		stop_ = false;
-		for (int w = 0; w < n; w++) threads_.emplace_back([this, w] { loop(w); });
+		const unsigned long long now = generation_;
+		for (int w = 0; w < n; w++) threads_.emplace_back([this, w, now] { loop(w, now); });
 	}
 	void submit(std::function<void(int)> fn) {            // not re-entrant: wait() first
 		std::lock_guard<std::mutex> lk(m_);
@@ -169,6 +169,7 @@ struct ReadbackHost {
 	int n_slices = 0;
 	std::atomic<int> next{0};
 	std::atomic<bool> cancel{false};
+	std::atomic<bool> go{false};             // set from the stream (cudaLaunchHostFunc) once the upload has left host memory alone
 	std::vector<unsigned char> zeroed;       // per slice; a worker sets its slices' flags before it returns
 };
 
@@ -198,7 +199,12 @@ static void settle_prezero(ReadbackHost& H) {
 // A host entry point that expects a sparse table calls this before its first copy: the workers start streaming zeros over the host
 // table while the GPU is still busy with the upload and the voxelization; the read-back then only writes the lines that hold
 // non-zero words (and finishes whatever part of the zero-fill was still to do in the same pass as those lines).
-void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads) {
+// `after`: the stream position behind which the zero-fill may start — behind the upload's host-to-device copies, because the
+// streaming stores and the copy engine's reads of host memory slow each other down (measured: a 3.3 ms upload took 7.1 ms next
+// to eight zero-filling threads, and the whole call got slower); nullptr... is not a stream here: pass the stream the copies are on.
+static void CUDART_CB prezero_go(void* flag) { static_cast<std::atomic<bool>*>(flag)->store(true); }
+
+void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after) {
 	static const bool off = getenv("VOXB200_NO_PREZERO") != nullptr;
 	if (off || !sparse_eligible(nullptr, words, host_table)) return;
 	ReadbackHost& H = host_of(rb);
@@ -208,9 +214,10 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 	const size_t blocks = (words + kNzBlockWords - 1) / kNzBlockWords;
 	H.table = host_table; H.words = words; H.n_slices = slices_for(blocks);
 	H.zeroed.assign((size_t)H.n_slices, 0);
-	H.next = 0; H.cancel = false; H.active = true;
+	H.next = 0; H.cancel = false; H.go = false; H.active = true;
 	ReadbackHost* h = &H;
 	H.pool.submit([h, blocks](int) {
+		while (!h->go.load() && !h->cancel.load()) std::this_thread::sleep_for(std::chrono::microseconds(20));
 		for (;;) {
 			if (h->cancel.load()) break;
 			const int s = h->next.fetch_add(1);
@@ -222,6 +229,7 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 			h->zeroed[(size_t)s] = 1;
 		}
 	});
+	if (cudaLaunchHostFunc(after, prezero_go, &H.go) != cudaSuccess) { cudaGetLastError(); H.go = true; }
 }
 
 // Stops a zero-fill that is still running ahead (error paths: nobody may write the caller's table after the call has returned).
@@ -238,6 +246,7 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 	auto since = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
 	ReadbackHost& H = host_of(rb);
 	const bool prezero = H.active && H.table == host_table && H.words == words;
+	if (prezero) H.go = true;                             // (the stream has long passed the upload)
 	if (H.active && !prezero) settle_prezero(H);          // somebody else's table: just stop it
 	auto dense = [&]() -> int { settle_prezero(H); return dense_copy(rb, d_table, words, host_table, st); };
 	if (!sparse_eligible(d_table, words, host_table)) return dense();
@@ -322,6 +331,38 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 }
 
 }  // namespace voxb
+
+// Diagnostics: the host-thread machinery of the read-back without a GPU (the CPU test-suite calls it): a zero-fill that runs ahead,
+// cancelled, restarted with another thread count, and the two expansion passes over what it left.  0 = ok.
+extern "C" int voxb200_selftest_host_pool(void) {
+	using namespace voxb;
+	const size_t words = (size_t)kNzBlockWords * 64 * 5;
+	std::vector<unsigned int> raw(words + 16, 0xdeadbeefu);
+	unsigned int* table = raw.data() + ((64 - (reinterpret_cast<uintptr_t>(raw.data()) & 63u)) & 63u) / 4;
+	const int saved = g_readback_mode.load();
+	g_readback_mode = 2;
+	Readback rb;
+	int rc = 0;
+	for (int round = 0; round < 6 && rc == 0; round++) {
+		const int threads = 1 + (round * 3) % 5;                  // 1, 4, 2, 5, 3, 1: the pool is rebuilt every round
+		for (size_t i = 0; i < words; i++) table[i] = 0xdeadbeefu;
+		ReadbackHost& H = host_of(rb);
+		readback_prezero(rb, table, words, threads, nullptr);      // without a device the host function cannot be enqueued: starts at once
+		if (round & 1) std::this_thread::sleep_for(std::chrono::milliseconds(2));
+		settle_prezero(H);
+		// finish by hand what readback_table would do: full pass over the slices that were not reached, nothing for the others
+		const size_t blocks = words / kNzBlockWords;
+		for (int s = 0; s < H.n_slices; s++) {
+			const size_t w0 = blocks * (size_t)s / (size_t)H.n_slices * kNzBlockWords, w1 = blocks * (size_t)(s + 1) / (size_t)H.n_slices * kNzBlockWords;
+			if (!H.zeroed[(size_t)s]) readback_expand_slice(table, w0, w1, nullptr, 0, 0, false);
+		}
+		for (size_t i = 0; i < words; i++) if (table[i] != 0u) { rc = 1 + round; break; }
+		if (raw[0] != 0xdeadbeefu && table != raw.data()) rc = 100;
+	}
+	readback_free(rb);
+	g_readback_mode = saved;
+	return rc;
+}
 
 extern "C" int voxb200_set_host_threads(int n) {
 	if (n < 0 || n > 256) return voxb::abi_fail(VOXB200_EINVAL, "host threads: 0 = default, 1..256 (got %d)", n);

@@ -207,6 +207,8 @@ int voxb200_last_readback(uint64_t info[2]);
 int voxb200_set_readback_mode(int mode);
 /* Host threads of the sparse read-back: 0 = default (VOXB200_HOST_THREADS, else half the hardware threads, at most 16).  Process-wide. */
 int voxb200_set_host_threads(int n);
+/* Diagnostics: exercises the read-back's host-thread machinery (no GPU needed).  0 = ok. */
+int voxb200_selftest_host_pool(void);
 
 /* ---- multi-GPU: one process, one host thread per device ------------------------------------------------------ */
 /*

@@ -211,3 +211,12 @@ def test_readback_host_expansion_rebuilds_the_table(vb):
             fn(table.ctypes.data, cut, words, pairs.ctypes.data, pc, len(idx), True)
             assert np.array_equal(table, want), (density, sym)
             assert raw[off + words] == 0xDEADBEEF and (off == 0 or raw[off - 1] == 0xDEADBEEF)
+
+
+def test_readback_host_pool_selftest(vb):
+    """The read-back's worker pool — started, cancelled, rebuilt with other thread counts — and the zero-fill that runs ahead
+    (a rebuilt pool once ran the previous job again and hung the call: csrc/readback.cu HostPool)."""
+    from cuda_voxelizer_b200 import _lib
+    code = "import ctypes,sys; L=ctypes.CDLL(%r); sys.exit(L.voxb200_selftest_host_pool())" % _lib.SO_PATH
+    r = subprocess.run([os.sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
