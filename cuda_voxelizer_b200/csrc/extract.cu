@@ -47,23 +47,41 @@ __global__ void __launch_bounds__(kExtBlock) extract_count_kernel(const unsigned
 	if (threadIdx.x == 0) block_counts[blockIdx.x] = total;
 }
 
-// one CTA of 1024 threads: exclusive scan of n block counts into 64-bit offsets; offsets[n] = total
+// one CTA of 1024 threads: exclusive scan of n block counts (each < 2^17) into 64-bit offsets; offsets[n] = total.
+// Rounds of 1024 consecutive counts — coalesced loads, the next round's value fetched before this round's scan — instead of one
+// contiguous chunk per thread (whose strided 4-byte loads made the kernel latency-bound: 228 us for the 131,072 counts of a 1 GiB
+// table, more than the pass that produced them).
 __global__ void __launch_bounds__(1024) extract_scan_kernel(const unsigned int* __restrict__ counts, unsigned long long* __restrict__ offsets, size_t n) {
-	__shared__ unsigned long long part[1024];
-	const size_t per = (n + 1023) / 1024;
-	const size_t a = (size_t)threadIdx.x * per, b = a + per < n ? a + per : n;
-	unsigned long long s = 0;
-	for (size_t i = a; i < b; i++) s += counts[i];
-	part[threadIdx.x] = s;
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		unsigned long long run = 0;
-		for (int t = 0; t < 1024; t++) { const unsigned long long v = part[t]; part[t] = run; run += v; }
-		offsets[n] = run;
+	__shared__ unsigned int warp_total[32];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	unsigned long long base = 0;
+	unsigned int next = threadIdx.x < n ? counts[threadIdx.x] : 0u;
+	for (size_t r = 0; r < n; r += 1024) {
+		const unsigned int c = next;
+		const size_t ahead = r + 1024 + threadIdx.x;
+		next = ahead < n ? counts[ahead] : 0u;
+		unsigned int inc = c;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned int up = __shfl_up_sync(0xffffffffu, inc, d);
+			if (lane >= d) inc += up;
+		}
+		if (lane == 31) warp_total[wid] = inc;
+		__syncthreads();
+		unsigned int wt = warp_total[lane];                     // every warp scans the 32 warp totals itself
+		unsigned int winc = wt;
+#pragma unroll
+		for (int d = 1; d < 32; d <<= 1) {
+			const unsigned int up = __shfl_up_sync(0xffffffffu, winc, d);
+			if (lane >= d) winc += up;
+		}
+		const unsigned int warp_base = __shfl_sync(0xffffffffu, winc - wt, wid);
+		const unsigned int round_total = __shfl_sync(0xffffffffu, winc, 31);
+		if (r + threadIdx.x < n) offsets[r + threadIdx.x] = base + warp_base + (inc - c);
+		base += round_total;
+		__syncthreads();
 	}
-	__syncthreads();
-	unsigned long long run = part[threadIdx.x];
-	for (size_t i = a; i < b; i++) { offsets[i] = run; run += counts[i]; }
+	if (threadIdx.x == 0) offsets[n] = base;
 }
 
 __global__ void __launch_bounds__(kExtBlock) extract_write_kernel(const unsigned int* __restrict__ table, size_t n_words,

@@ -133,7 +133,7 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 	// a tile whose run would keep one CTA busy for a large part of the whole kernel is not binned: its triangles take the side path
 	const unsigned int cap = (unsigned int)(n / 256 > 8192 ? n / 256 : 8192);
 	cudaError_t e = launch_tile_count(g, tg, d_soup, d_verts, d_faces, m.keys, m.cnt, m.totals, st);
-	if (e == cudaSuccess) e = launch_tile_plan(tg, cap, m.cnt, m.off, m.order, m.work, m.empty, m.totals, st);
+	if (e == cudaSuccess) e = launch_tile_plan(tg, cap, m.cnt, m.off, m.order, m.work, m.empty, m.totals, m.fill, st);      // fill: free until the scatter clears it
 	if (e == cudaSuccess) e = cudaMemcpyAsync(m.host_totals, m.totals, sizeof(m.host_totals), cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) return abi_fail_cuda(e, "voxb200_mesh prepare (count / plan)");

@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(kPrepBlock) tile_count_kernel(const GridParams
 __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, const unsigned int cap, const unsigned int* __restrict__ cnt,
                                                          unsigned int* __restrict__ off, unsigned int* __restrict__ order,
                                                          uint4* __restrict__ work, unsigned int* __restrict__ empty,
-                                                         unsigned long long* __restrict__ totals) {
+                                                         unsigned long long* __restrict__ totals, unsigned int* __restrict__ order_cnt) {
 	__shared__ unsigned long long s_inst[1024];
 	__shared__ unsigned int s_empty[1024], s_work[1024], s_batches[1024];
 	__shared__ unsigned int s_bin[kLptBins], s_cursor[kLptBins];
@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, cons
 	__syncthreads();
 	unsigned long long inst = 0ull, heavy = 0ull;
 	unsigned int n_empty = 0u, n_work = 0u;
+#pragma unroll 8
 	for (unsigned int t = a; t < b; t++) {
 		const unsigned int raw = cnt[t];
 		const unsigned int c = raw > cap ? 0u : raw;
@@ -181,7 +182,9 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, cons
 				empty[re++] = (unsigned int)((((unsigned long long)tzl * kTileZ * G + (unsigned long long)ty * kTileY) * G + ((unsigned long long)tx << tg.tx_shift)) >> 5);
 			} else {
 				const unsigned int bin = min(c >> 3, (unsigned int)kLptBins - 1u);
-				order[s_bin[bin] + atomicAdd(&s_cursor[bin], 1u)] = t;
+				const unsigned int slot = s_bin[bin] + atomicAdd(&s_cursor[bin], 1u);
+				order[slot] = t;
+				order_cnt[slot] = c;                 // the later passes walk the work order: no dependent load through order[]
 			}
 		}
 	}
@@ -192,7 +195,8 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, cons
 	const unsigned int perw = (nw + 1023u) / 1024u;
 	const unsigned int wa = min(nw, threadIdx.x * perw), wb = min(nw, wa + perw);
 	unsigned int nb = 0u;
-	for (unsigned int w = wa; w < wb; w++) { const unsigned int c = cnt[order[w]]; nb += (c + 31u) >> 5; }
+#pragma unroll 8
+	for (unsigned int w = wa; w < wb; w++) nb += (order_cnt[w] + 31u) >> 5;
 	s_batches[threadIdx.x] = nb;
 	__syncthreads();
 	if (threadIdx.x == 0) {
@@ -202,9 +206,10 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, cons
 	}
 	__syncthreads();
 	unsigned int run = s_batches[threadIdx.x];
+#pragma unroll 4
 	for (unsigned int w = wa; w < wb; w++) {
 		// everything a tile block needs, in one 16-byte load: {table word of the tile's first voxel, records, first record, batches before it}
-		const unsigned int t = order[w], c = cnt[t];
+		const unsigned int t = order[w], c = order_cnt[w];
 		const unsigned int tx = t % (unsigned int)tg.ntx, r = t / (unsigned int)tg.ntx;
 		const unsigned int ty = r % (unsigned int)tg.nty, tzl = r / (unsigned int)tg.nty;
 		const unsigned long long G = (unsigned long long)tg.G;
@@ -298,8 +303,8 @@ cudaError_t launch_tile_count(const GridParams& g, const TileGeom& tg, const flo
 }
 
 cudaError_t launch_tile_plan(const TileGeom& tg, unsigned int cap, const unsigned int* d_cnt, unsigned int* d_off, unsigned int* d_order,
-                             void* d_work, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st) {
-	tile_plan_kernel<<<1, 1024, 0, st>>>(tg, cap, d_cnt, d_off, d_order, reinterpret_cast<uint4*>(d_work), d_empty, d_totals);
+                             void* d_work, unsigned int* d_empty, unsigned long long* d_totals, unsigned int* d_scratch, cudaStream_t st) {
+	tile_plan_kernel<<<1, 1024, 0, st>>>(tg, cap, d_cnt, d_off, d_order, reinterpret_cast<uint4*>(d_work), d_empty, d_totals, d_scratch);
 	g_launch_count++;
 	return cudaGetLastError();
 }

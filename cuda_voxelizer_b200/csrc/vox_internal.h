@@ -143,7 +143,7 @@ struct TilePlan {
 cudaError_t launch_tile_count(const GridParams& g, const TileGeom& tg, const float* d_soup, const float* d_verts, const int* d_faces,
                               unsigned int* d_keys, unsigned int* d_cnt, unsigned long long* d_totals, cudaStream_t st);
 cudaError_t launch_tile_plan(const TileGeom& tg, unsigned int cap, const unsigned int* d_cnt, unsigned int* d_off, unsigned int* d_order,
-                             void* d_work, unsigned int* d_empty, unsigned long long* d_totals, cudaStream_t st);
+                             void* d_work, unsigned int* d_empty, unsigned long long* d_totals, unsigned int* d_scratch, cudaStream_t st);      // d_scratch: n_tiles words
 cudaError_t launch_tile_scatter(const GridParams& g, const TileGeom& tg, unsigned int cap, const float* d_soup, const float* d_verts,
                                 const int* d_faces, const unsigned int* d_keys, const unsigned int* d_cnt, const unsigned int* d_off,
                                 unsigned int* d_fill, void* d_records, float* d_side, unsigned long long* d_totals, cudaStream_t st);

@@ -49,3 +49,28 @@ for _ in range(2):
     assert np.array_equal(vb.voxelize_solid(grid, d).cpu().numpy().view(np.uint32), want)
 assert vb.last_counters()["solid_row_lists"] == 1
 print("sanitize run ok")
+# round 2: prepared mesh (tile schedule) with update, binvox encoder, sparse read-back (forced: the tables here are small)
+v, f = cases.mesh("icosphere:64:128")
+soup = oracle.soup(v, f)
+d = torch.from_numpy(soup).cuda()
+grid = vb.grid_from_verts(v, 256, len(f))
+ref = vb.voxelize(grid, d)
+m = vb.Mesh(grid, tris=d)
+assert m.info()["tile_schedule"] == 1
+assert torch.equal(m.voxelize(), ref)
+m.update(tris=d)
+assert torch.equal(m.voxelize(), ref)
+mi = vb.Mesh(grid, verts=torch.from_numpy(np.ascontiguousarray(v)).cuda(), faces=torch.from_numpy(np.ascontiguousarray(f)).cuda())
+assert torch.equal(mi.voxelize(), ref)
+m.close(); mi.close()
+payload = vb.binvox_rle(ref, 256)
+assert len(payload) % 2 == 0 and int(payload[1::2].astype(np.int64).sum()) == 256 ** 3
+vb.set_readback_mode("sparse")
+host = torch.full((ref.numel(),), -1, dtype=torch.int32).pin_memory()
+_, info = vb.download_table(ref, host)
+assert info["sparse"] and torch.equal(host, ref.cpu())
+host.fill_(-1)
+vb.voxelize_host_indexed(grid, torch.from_numpy(np.ascontiguousarray(v)).pin_memory(), torch.from_numpy(np.ascontiguousarray(f)).pin_memory(), host)
+assert torch.equal(host, ref.cpu())
+vb.set_readback_mode("auto")
+print("sanitize.py: all paths ok")
