@@ -18,7 +18,8 @@ calls (one captured CUDA graph replayed K times), so the preparation is inside t
 steps the command line asks for.  The line also carries "resident" (the K steps alone), "prepare_ms", and "one_shot"
 (voxb200_surface on the caller's order: what a single voxelization without preparation costs).
   value : Mtri/s with triangles resident in HBM (device time, CUDA events, max over ranks)
-  e2e   : Mtri/s through voxb200_voxelize_host_indexed — pinned host mesh -> H2D -> tile records -> voxelize -> D2H of the slab
+  e2e   : Mtri/s through voxb200_voxelize_host_indexed — pinned host mesh -> H2D -> tile records -> voxelize -> the table in pinned
+          host memory (dense D2H, or the non-zero words + host-thread expansion: voxb200_download_table); N > 1: voxb200_voxelize_host_multi
 """
 import argparse
 import json
