@@ -216,8 +216,10 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 	H.zeroed.assign((size_t)H.n_slices, 0);
 	H.next = 0; H.cancel = false; H.go = false; H.active = true;
 	ReadbackHost* h = &H;
-	H.pool.submit([h, blocks](int) {
-		while (!h->go.load() && !h->cancel.load()) std::this_thread::sleep_for(std::chrono::microseconds(20));
+	// a few workers start at once (a gentle stream of stores costs the upload little), the rest when the upload is through
+	static const int early = [] { const char* e = getenv("VOXB200_PREZERO_EARLY"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : v; }();
+	H.pool.submit([h, blocks](int w) {
+		while (w >= early && !h->go.load() && !h->cancel.load()) std::this_thread::sleep_for(std::chrono::microseconds(20));
 		for (;;) {
 			if (h->cancel.load()) break;
 			const int s = h->next.fetch_add(1);
