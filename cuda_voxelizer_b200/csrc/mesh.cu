@@ -7,7 +7,8 @@
 // handles are re-entrant: different handles may voxelize concurrently on different streams.
 //
 // Two schedules, chosen at creation:
-//   TILES   surface, linear order, G a multiple of 256 (<= 4096), z-range on tile boundaries: surface_tile_kernel
+//   TILES   surface, linear order, G a multiple of 256 (of 1024 above 1024), a region of at most 2^32 words and 2^20 tiles (all of a
+//           4096^3 grid; 8192^3 in z-slabs of up to 2048 layers), z-range on tile boundaries: surface_tile_kernel
 //           writes every table byte once + launch_surface(ACCUMULATE) over the side soup.
 //   DIRECT  everything else (solid, morton, other grid sizes): the one-shot kernels on the handle's own copy of the
 //           soup (z-layer ordered for the surface path), with the handle's own workspace.
@@ -68,9 +69,14 @@ bool tileable(const voxb200_mesh& m) { return voxb::mesh_tileable(m.g, m.flags);
 namespace voxb {
 bool mesh_tileable(const GridParams& g, unsigned int flags) {
 	if (flags & (VOXB200_SOLID | VOXB200_MORTON)) return false;
-	if (g.G < 256 || g.G > 4096 || (g.G % (g.G < kTileXMax ? 256 : kTileXMax)) != 0 || (g.G < kTileXMax && (g.G & (g.G - 1)) != 0)) return false;
+	// coordinates travel as 16 bits in the records, word offsets inside the region as 32 (8192^3 in slabs of at most 2048 layers),
+	// tiles as 20 bits in the planning keys
+	if (g.G < 256 || g.G > 32768 || !g.w32 || (g.G % (g.G < kTileXMax ? 256 : kTileXMax)) != 0 || (g.G < kTileXMax && (g.G & (g.G - 1)) != 0)) return false;
 	if (g.rx0 != 0 || g.rx1 != g.G || g.ry0 != 0 || g.ry1 != g.G) return false;
 	if ((g.rz0 % kTileZ) != 0 || (g.rz1 % kTileZ) != 0) return false;
+	const int tile_x = g.G < kTileXMax ? g.G : kTileXMax;
+	const unsigned long long tiles = (unsigned long long)(g.G / tile_x) * (unsigned long long)(g.G / kTileY) * (unsigned long long)((g.rz1 - g.rz0) / kTileZ);
+	if (tiles > (1ull << 20)) return false;
 	return true;
 }
 }  // namespace voxb

@@ -256,7 +256,7 @@ __device__ __forceinline__ bool load_tile_tri(const GridParams& g, const float* 
 template <bool MORTON>
 __device__ __forceinline__ void scatter_hits4(unsigned long long hit, int x0, int y0, int z0, const GridParams& g,
                                               unsigned int* __restrict__ table) {
-	const bool fast = !MORTON && (g.G & 31) == 0 && g.G <= 4096;
+	const bool fast = !MORTON && (g.G & 31) == 0 && g.w32;
 	const unsigned int Gw = (unsigned int)g.G >> 5;
 	const unsigned int w0 = fast ? Gw * ((unsigned int)y0 + (unsigned int)g.G * (unsigned int)z0) + ((unsigned int)x0 >> 5) - (unsigned int)g.word_base : 0u;
 	const unsigned int sh = (unsigned int)x0 & 31u;
@@ -302,8 +302,9 @@ __device__ __forceinline__ void scatter_hits3(unsigned int hit, int x0, int y0, 
 		if (mask) atomicOr(table + cur, mask);
 		return;
 	}
-	if ((g.G & 31) == 0 && g.G <= 4096) {
-		// rows are whole words and every word offset fits 32 bits: all-integer-32 addressing
+	if ((g.G & 31) == 0 && g.w32) {
+		// rows are whole words and every word offset INSIDE THE REGION fits 32 bits: all-integer-32 addressing.  The absolute word
+		// index may not (8192^3: 2^34 words) — the products below wrap modulo 2^32, and so does word_base: the difference is exact.
 		const unsigned int Gw = (unsigned int)g.G >> 5;
 		const unsigned int w0 = Gw * ((unsigned int)y0 + (unsigned int)g.G * (unsigned int)z0) + ((unsigned int)x0 >> 5) - (unsigned int)g.word_base;
 		const unsigned int sh = (unsigned int)x0 & 31u;

@@ -143,7 +143,7 @@ __device__ __forceinline__ void tri_tile(const GridParams& g, const float* __res
 		if (hit4) scatter_hits4<MORTON>(hit4, s.x0, s.y0, s.z0, g, table);
 		return;
 	}
-	if (!MORTON && (g.G & 31) == 0 && g.G <= 4096) {
+	if (!MORTON && (g.G & 31) == 0 && g.w32) {
 		if (!mine) { s.x0 = 0; s.y0 = 0; s.z0 = 0; }
 		scatter_hits3<MORTON>(hit, s.x0, s.y0, s.z0, g, table);     // converged: every write is predicated on its own bits
 		return;

@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(1024) tile_plan_kernel(const TileGeom tg, cons
 			off[t] = (unsigned int)ri;
 			ri += c;
 			if (c == 0u) {
-				// the table word (relative to the region) of the tile's first voxel: G <= 4096, so it fits 32 bits
+				// the table word (relative to the region) of the tile's first voxel: the region holds at most 2^32 words (mesh_tileable)
 				const unsigned int tx = t % (unsigned int)tg.ntx, r = t / (unsigned int)tg.ntx;
 				const unsigned int ty = r % (unsigned int)tg.nty, tzl = r / (unsigned int)tg.nty;
 				const unsigned long long G = (unsigned long long)tg.G;

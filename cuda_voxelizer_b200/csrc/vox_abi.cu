@@ -82,7 +82,7 @@ unsigned int compact3(unsigned long long m) {   // inverse of spread3
 }
 
 // Validates the region and derives {word_base, region_words}.
-int resolve_region(const voxb200_grid* grid, const voxb200_region* region, bool morton, GridParams* g, size_t* region_words) {
+static int resolve_region_impl(const voxb200_grid* grid, const voxb200_region* region, bool morton, GridParams* g, size_t* region_words) {
 	const unsigned int G = grid->gridsize[0];
 	if (G == 0 || grid->gridsize[1] != G || grid->gridsize[2] != G)
 		return fail(VOXB200_EINVAL, "grid must be cubic and non-empty (got %u %u %u); the reference only builds cubic grids (main.cpp:186)",
@@ -132,6 +132,13 @@ int resolve_region(const voxb200_grid* grid, const voxb200_region* region, bool 
 	g->word_base = first >> 5;
 	*region_words = (size_t)(1ull << (a + b + c - 5));
 	return VOXB200_OK;
+}
+// + w32: region-relative word offsets fit 32 bits (the 32-bit addressing of the scatter and tile code)
+int resolve_region(const voxb200_grid* grid, const voxb200_region* region, bool morton, GridParams* g, size_t* region_words) {
+	g->w32 = 0;
+	const int rc = resolve_region_impl(grid, region, morton, g, region_words);
+	if (rc == VOXB200_OK) g->w32 = *region_words <= 0x100000000ull ? 1 : 0;
+	return rc;
 }
 
 int run_path(bool solid, const voxb200_grid* grid, const float* d_tris, unsigned int* d_table, unsigned int flags,

@@ -27,6 +27,7 @@ struct GridParams {
 	int rz0, rz1;
 	unsigned long long word_base;   // index of the table word holding the region's first voxel
 	unsigned long long n_tris;
+	int w32;                   // the region's words fit 32 bits: region-relative word offsets may be computed modulo 2^32
 };
 
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }

@@ -62,6 +62,8 @@ def lib():
             fn.argtypes = [_f32p, C.c_size_t, _f32p, _f32p, C.c_uint, C.c_int, C.c_int, C.c_int, _u32p, C.c_void_p]
             fn.restype = None
         L.oracle_solid_ub_events.restype = C.c_uint64
+        L.oracle_set_table_origin.argtypes = [C.c_size_t]
+        L.oracle_set_table_origin.restype = None
         L.oracle_expand_soup.argtypes = [_f32p, _i32p, C.c_size_t, _f32p]
         L.oracle_fnv1a64.argtypes = [C.c_void_p, C.c_size_t]
         L.oracle_fnv1a64.restype = C.c_uint64
@@ -145,6 +147,19 @@ def surface(tris, bb_min, unit, gridsize, morton=False, z_range=None, table=None
 def solid(tris, bb_min, unit, gridsize, morton=False, z_range=None, table=None, return_stats=False):
     t, s = _run(lib().oracle_solid, tris, bb_min, unit, gridsize, morton, z_range, table)
     return (t, s) if return_stats else t
+
+
+def surface_slab(tris, bb_min, unit, gridsize, z0, z1):
+    """The words of z-slab [z0, z1) of the LINEAR surface table of a grid that may be too big for host memory as a whole
+    (8192^3 = 64 GiB): the oracle run clipped to the slab, writing into a slab-sized table."""
+    words_per_layer = gridsize * gridsize // 32
+    table = np.zeros(words_per_layer * (z1 - z0), np.uint32)
+    lib().oracle_set_table_origin(words_per_layer * z0)
+    try:
+        surface(tris, bb_min, unit, gridsize, z_range=(z0, z1), table=table)
+    finally:
+        lib().oracle_set_table_origin(0)
+    return table
 
 
 def solid_ub_events():

@@ -131,14 +131,19 @@ uint64_t oracle_morton(unsigned int x, unsigned int y, unsigned int z) {
 }
 
 /* ------------------------------------------------------------------ bit table (cpu_voxelizer.cpp:7-15,186-194) */
+/* Test harness only: a table that holds just a z-slab of a grid too big for host memory (8192^3 = 64 GiB) starts at this word of
+ * the full table; 0 (the default) = the whole table, as in the reference. */
+static size_t g_table_origin = 0;
+void oracle_set_table_origin(size_t first_word) { g_table_origin = first_word; }
+
 static inline void set_bit(uint32_t* table, size_t index) {
-	size_t w = index / 32;
+	size_t w = index / 32 - g_table_origin;
 	uint32_t mask = 1u << (31 - (uint32_t)(index % 32));
 #pragma omp atomic
 	table[w] |= mask;
 }
 static inline void xor_bit(uint32_t* table, size_t index) {
-	size_t w = index / 32;
+	size_t w = index / 32 - g_table_origin;
 	uint32_t mask = 1u << (31 - (uint32_t)(index % 32));
 #pragma omp atomic
 	table[w] ^= mask;

@@ -111,3 +111,15 @@ def test_morton_table_is_permutation_of_linear():
     mbits = np.unpackbits(mor.view(np.uint8).reshape(-1, 4)[:, ::-1].reshape(-1))
     midx = np.array([oracle.morton(a, b, c) for a, b, c in zip(x, y, z)])
     assert mbits.sum() == len(midx) and mbits[midx].all()
+
+
+def test_slab_mode_equals_the_words_of_the_full_table():
+    """oracle.surface_slab (a slab-sized table with an origin: what the 8192^3 GPU tests compare against) against the full run."""
+    v, f = cases.mesh("bunny")
+    mn, mx, unit = oracle.voxinfo(v, 128)
+    soup = oracle.soup(v, f)
+    full = oracle.surface(soup, mn, unit, 128)
+    w = 128 * 128 // 32
+    for z0, z1 in ((0, 16), (48, 96), (112, 128)):
+        assert np.array_equal(oracle.surface_slab(soup, mn, unit, 128, z0, z1), full[z0 * w: z1 * w])
+    assert np.array_equal(oracle.surface(soup, mn, unit, 128), full)        # the origin is back at 0
