@@ -195,10 +195,19 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    cpu_group = dist.new_group(backend="gloo") if world > 1 else None
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def cpu_barrier():
+        """A wait that leaves the GPUs alone: an NCCL barrier parks a spinning kernel on every waiting rank's device, which is in the
+        way when ONE rank drives all devices (voxb200_voxelize_host_multi) while the others wait."""
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     wname = args.workload
     w = WORKLOADS[wname]
@@ -384,7 +393,7 @@ def run_ours(args):
     # The other ranks wait at the barrier (their GPUs are idle while rank 0's threads use them).
     multi = None
     if world > 1:
-        barrier()
+        cpu_barrier()
         if rank == 0:
             full_table = torch.empty(vb.table_bytes(G) // 4, dtype=torch.int32).pin_memory()
             for _ in range(2):
@@ -402,7 +411,7 @@ def run_ours(args):
                      "table": full_table}
             torch.cuda.set_device(local_rank)
             vb.init(local_rank)
-        barrier()
+        cpu_barrier()
     # device-event total per step (H2D start -> D2H end), max over ranks; wall kept alongside
     te = torch.tensor([e2e_dev_ms / e2e_steps, e2e_wall_ms / e2e_steps], dtype=torch.float64, device="cuda")
     if world > 1:
