@@ -147,7 +147,7 @@ void worker(Shared& S, int d) {
 	if (vhi > vlo) STEP(cudaMemcpyAsync((char*)D.d_verts + vlo, (const char*)S.host_verts + vlo, vhi - vlo, cudaMemcpyHostToDevice, st));
 	if (fhi > flo) STEP(cudaMemcpyAsync((char*)D.d_faces + flo, (const char*)S.host_faces + flo, fhi - flo, cudaMemcpyHostToDevice, st));
 	STEP(cudaEventRecord(D.ev[1], st));
-	if (!S.failed && !solid) readback_prezero(D.rb, host_slab, S.slab_bytes[d] / sizeof(unsigned int), back_threads, st);      // see voxb200_voxelize_host
+	if (!S.failed && !solid) readback_prezero(D.rb, host_slab, S.slab_bytes[d] / sizeof(unsigned int), back_threads, st, S.n == 1);      // see voxb200_voxelize_host
 	S.barrier.arrive_and_wait();                 // all share-done events are recorded
 	// 2. all-gather of the shares, device to device
 	for (int k = 1; k < S.n && !S.failed; k++) {

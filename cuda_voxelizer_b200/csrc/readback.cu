@@ -204,7 +204,7 @@ static void settle_prezero(ReadbackHost& H) {
 // to eight zero-filling threads, and the whole call got slower); nullptr... is not a stream here: pass the stream the copies are on.
 static void CUDART_CB prezero_go(void* flag) { static_cast<std::atomic<bool>*>(flag)->store(true); }
 
-void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after) {
+void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after, bool allow_early) {
 	static const bool off = getenv("VOXB200_NO_PREZERO") != nullptr;
 	if (off || !sparse_eligible(nullptr, words, host_table)) return;
 	ReadbackHost& H = host_of(rb);
@@ -217,8 +217,9 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 	H.next = 0; H.cancel = false; H.go = false; H.active = true;
 	ReadbackHost* h = &H;
 	// a few workers start at once (a gentle stream of stores costs the upload little), the rest when the upload is through
-	static const int early = [] { const char* e = getenv("VOXB200_PREZERO_EARLY"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : v; }();
-	H.pool.submit([h, blocks](int w) {
+	static const int early_default = [] { const char* e = getenv("VOXB200_PREZERO_EARLY"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : v; }();
+	const int early = allow_early ? early_default : 0;      // (several devices upload at once: every early worker is one too many, measured)
+	H.pool.submit([h, blocks, early](int w) {
 		while (w >= early && !h->go.load() && !h->cancel.load()) std::this_thread::sleep_for(std::chrono::microseconds(20));
 		for (;;) {
 			if (h->cancel.load()) break;
@@ -349,7 +350,7 @@ extern "C" int voxb200_selftest_host_pool(void) {
 		const int threads = 1 + (round * 3) % 5;                  // 1, 4, 2, 5, 3, 1: the pool is rebuilt every round
 		for (size_t i = 0; i < words; i++) table[i] = 0xdeadbeefu;
 		ReadbackHost& H = host_of(rb);
-		readback_prezero(rb, table, words, threads, nullptr);      // without a device the host function cannot be enqueued: starts at once
+		readback_prezero(rb, table, words, threads, nullptr, true);      // without a device the host function cannot be enqueued: starts at once
 		if (round & 1) std::this_thread::sleep_for(std::chrono::milliseconds(2));
 		settle_prezero(H);
 		// finish by hand what readback_table would do: full pass over the slices that were not reached, nothing for the others

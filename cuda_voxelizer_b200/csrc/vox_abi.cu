@@ -651,7 +651,7 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 	CU(cudaEventRecord(hp.ev[0], st));
 	rc = h2d(hp, hp.d_tris, host_tris9, tris_bytes, st);
 	if (rc) return rc;
-	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0, st);      // surface tables are sparse: zero-fill the host table meanwhile
+	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0, st, true);      // surface tables are sparse: zero-fill the host table meanwhile
 	CU(cudaEventRecord(hp.ev[1], st));
 	const unsigned int path_flags = flags & (VOXB200_MORTON);
 	rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, path_flags, region, st);
@@ -694,7 +694,7 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 	rc = h2d(hp, hp.d_verts, host_verts, n_verts * 3 * sizeof(float), st);
 	if (!rc) rc = h2d(hp, hp.d_faces, host_faces, n_faces * 3 * sizeof(int), st);
 	if (rc) return rc;
-	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0, st);      // surface tables are sparse: zero-fill the host table meanwhile
+	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0, st, true);      // surface tables are sparse: zero-fill the host table meanwhile
 	if (tiles) {
 		const bool same = hp.mesh && memcmp(&hp.mesh_grid, grid, sizeof(*grid)) == 0 && hp.mesh_has_region == (region != nullptr) &&
 		                  (!region || memcmp(&hp.mesh_region, region, sizeof(*region)) == 0);

@@ -189,7 +189,7 @@ struct Readback {
 int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsigned int* host_table, cudaStream_t st, int host_threads);
 // Optional, in a call whose table is expected to be sparse: host threads zero-fill host_table ahead of the read-back, starting when
 // `after` has passed the point it is at now (enqueue it behind the upload's copies).
-void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after);
+void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after, bool allow_early);
 void readback_cancel(Readback& rb);          // every exit of a call that started one (idempotent)
 struct ReadbackGuard { Readback& rb; ~ReadbackGuard() { readback_cancel(rb); } };
 void readback_free(Readback& rb);
