@@ -23,7 +23,7 @@ EXPORTS = [
     "voxb200_route_triangles", "voxb200_voxelize_host_indexed", "voxb200_route_triangles_multi", "voxb200_extract_voxels", "voxb200_release", "voxb200_sort_triangles",
     "voxb200_reference_table_bytes", "voxb200_mesh_create", "voxb200_mesh_create_indexed", "voxb200_mesh_update", "voxb200_mesh_update_indexed",
     "voxb200_mesh_voxelize", "voxb200_mesh_info", "voxb200_mesh_destroy", "voxb200_mesh_counters",
-    "voxb200_voxelize_host_multi", "voxb200_gather_slabs", "voxb200_host_alloc", "voxb200_host_free", "voxb200_download_table", "voxb200_binvox_rle", "voxb200_last_readback", "voxb200_set_readback_mode", "voxb200_set_host_threads", "voxb200_selftest_host_pool",
+    "voxb200_voxelize_host_multi", "voxb200_gather_slabs", "voxb200_host_alloc", "voxb200_host_free", "voxb200_download_table", "voxb200_voxelize_host_nonzero", "voxb200_binvox_rle", "voxb200_last_readback", "voxb200_set_readback_mode", "voxb200_set_host_threads", "voxb200_selftest_host_pool",
 ]
 
 
@@ -104,6 +104,7 @@ def lib():
     L.voxb200_set_readback_mode.argtypes = [C.c_int]
     L.voxb200_set_host_threads.argtypes = [C.c_int]
     L.voxb200_binvox_rle.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_void_p]
+    L.voxb200_voxelize_host_nonzero.argtypes = [C.POINTER(Grid), C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), f3]
     L.voxb200_last_readback.argtypes = [C.POINTER(C.c_uint64)]
     L.voxb200_download_table.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
     L.voxb200_launch_count.argtypes = [C.c_int]

@@ -255,6 +255,22 @@ def voxelize_host_indexed(grid, host_verts, host_faces, host_table=None, solid=F
     return host_table, [float(t) for t in timing]
 
 
+def voxelize_host_nonzero(grid, host_verts, host_faces, solid=False, morton=False, region=None):
+    """voxb200_voxelize_host_nonzero: end to end from the indexed mesh to the table's non-zero words.  Returns (pairs, timing_ms):
+    pairs = uint32 array [n, 2] of {word index, bits}, ascending (a COPY of the library's pinned buffer)."""
+    def ptr(a):
+        return a.data_ptr() if hasattr(a, "data_ptr") else a.ctypes.data
+    n_verts = (host_verts.numel() if hasattr(host_verts, "numel") else host_verts.size) // 3
+    out, n = C.c_void_p(), C.c_size_t()
+    timing = (C.c_float * 4)()
+    flags = (MORTON if morton else 0) | (SOLID if solid else 0)
+    rp = C.byref(region) if region is not None else None
+    check(_lib.lib().voxb200_voxelize_host_nonzero(C.byref(grid), C.c_void_p(ptr(host_verts)), n_verts, C.c_void_p(ptr(host_faces)), flags, rp,
+                                                   C.byref(out), C.byref(n), timing))
+    pairs = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint32)), shape=(n.value, 2)).copy() if n.value else np.zeros((0, 2), np.uint32)
+    return pairs, [float(t) for t in timing]
+
+
 def route_triangles_multi(grid, tris, regions, out, solid=False, morton=False, stream=None):
     """Route a device soup to several regions at once into the preallocated CUDA tensor ``out`` (float32, capacity
     out.numel() // 9 triangles), segments back to back in region order.  Returns the per-region triangle counts."""

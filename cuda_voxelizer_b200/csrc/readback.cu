@@ -235,6 +235,43 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 	if (cudaLaunchHostFunc(after, prezero_go, &H.go) != cudaSuccess) { cudaGetLastError(); H.go = true; }
 }
 
+// The non-zero words alone: ascending {word index, value} pairs in the Readback's pinned host buffer (valid until its next call).
+int readback_pairs(Readback& rb, const unsigned int* d_table, size_t words, cudaStream_t st, const void** host_pairs, size_t* n_pairs) {
+	if (words > 0x100000000ull) return abi_fail(VOXB200_EINVAL, "a table of more than 2^32 words has no 32-bit word indices: voxelize it in regions");
+	if (reinterpret_cast<uintptr_t>(d_table) & 15u) return abi_fail(VOXB200_EINVAL, "the table must be 16-byte aligned");
+	const size_t blocks = (words + kNzBlockWords - 1) / kNzBlockWords;
+	if (blocks + 1 > rb.blocks_cap) {
+		size_t a = 0, b = 0;
+		RB_CU(grow_dev(&rb.d_counts, &a, blocks + 1));
+		RB_CU(grow_dev(&rb.d_offsets, &b, blocks + 1));
+		rb.blocks_cap = blocks + 1;
+	}
+	RB_CU(grow_pinned(&rb.h_offsets, &rb.h_blocks_cap, blocks + 1));
+	RB_CU(launch_nz_count(d_table, words, rb.d_counts, rb.d_offsets, st));
+	RB_CU(cudaMemcpyAsync(rb.h_offsets + blocks, rb.d_offsets + blocks, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+	RB_CU(cudaStreamSynchronize(st));
+	const unsigned long long nnz = rb.h_offsets[blocks];
+	if (nnz > rb.pairs_cap) {
+		uint2* p = reinterpret_cast<uint2*>(rb.d_pairs);
+		RB_CU(grow_dev(&p, &rb.pairs_cap, (size_t)(nnz + nnz / 4 + 1024)));
+		rb.d_pairs = p;
+	}
+	if (nnz > rb.h_pairs_cap) {
+		uint2* p = reinterpret_cast<uint2*>(rb.h_pairs);
+		RB_CU(grow_pinned(&p, &rb.h_pairs_cap, (size_t)(nnz + nnz / 4 + 1024)));
+		rb.h_pairs = p;
+	}
+	if (nnz) {
+		RB_CU(launch_nz_write(d_table, words, rb.d_offsets, rb.d_pairs, st));
+		RB_CU(cudaMemcpyAsync(rb.h_pairs, rb.d_pairs, (size_t)nnz * sizeof(uint2), cudaMemcpyDeviceToHost, st));
+	}
+	RB_CU(cudaStreamSynchronize(st));
+	rb.last_mode = 1; rb.last_nonzero = nnz;
+	*host_pairs = rb.h_pairs;
+	*n_pairs = (size_t)nnz;
+	return VOXB200_OK;
+}
+
 // Stops a zero-fill that is still running ahead (error paths: nobody may write the caller's table after the call has returned).
 void readback_cancel(Readback& rb) {
 	if (rb.host) settle_prezero(*static_cast<ReadbackHost*>(rb.host));

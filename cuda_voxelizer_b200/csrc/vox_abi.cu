@@ -33,6 +33,7 @@ struct HostPath {
 	bool buf_busy[2] = {false, false};     // a copy out of pinned[b] may still be in flight
 	int next_buf = 0;
 	Readback rb;                            // device table -> host table (readback.cu)
+	bool last_tiles = false;                // the last indexed host call took the tile schedule
 };
 HostPath g_hp[kMaxDevices];
 
@@ -665,20 +666,16 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 	return host_timing(hp, t_call, timing_ms);
 }
 
-int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
-                                  unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]) {
-	const auto t_call = std::chrono::steady_clock::now();
-	if (!grid || !host_table || !host_verts || (!host_faces && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
-	Workspace* ws;
-	int rc = current_ws(&ws);
-	if (rc) return rc;
-	HostPath& hp = g_hp[ws->device];
-	rc = ensure_host_path(hp);
-	if (rc) return rc;
+// Upload + prepare + voxelize of the host entry points that take an indexed mesh; the table is left in hp.d_table (region_words
+// words), events 0..2 are recorded.  host_table: where the dense table will go (nullptr when the caller wants the non-zero words).
+static int host_indexed_to_device(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
+                                  unsigned int* host_table, unsigned int flags, const voxb200_region* region, Workspace* ws, HostPath& hp,
+                                  size_t* region_words_out) {
 	GridParams g;
 	size_t region_words = 0;
-	rc = resolve_region(grid, region, (flags & VOXB200_MORTON) != 0, &g, &region_words);
+	int rc = resolve_region(grid, region, (flags & VOXB200_MORTON) != 0, &g, &region_words);
 	if (rc) return rc;
+	*region_words_out = region_words;
 	const size_t n_faces = grid->n_triangles;
 	const size_t table_bytes = region_words * sizeof(unsigned int);
 	// Surface, linear order, tileable grid: the upload path bins the faces straight into the tile records of a prepared mesh (no
@@ -689,12 +686,11 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 	if (!tiles && (rc = grow(&hp.d_tris, &hp.tris_bytes, n_faces * 9 * sizeof(float) + 16))) return rc;
 	if ((rc = grow(&hp.d_table, &hp.table_bytes, table_bytes))) return rc;
 	cudaStream_t st = hp.stream;
-	ReadbackGuard guard{hp.rb};
 	CU(cudaEventRecord(hp.ev[0], st));
 	rc = h2d(hp, hp.d_verts, host_verts, n_verts * 3 * sizeof(float), st);
 	if (!rc) rc = h2d(hp, hp.d_faces, host_faces, n_faces * 3 * sizeof(int), st);
 	if (rc) return rc;
-	if (!(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0, st, true);      // surface tables are sparse: zero-fill the host table meanwhile
+	if (host_table && !(flags & VOXB200_SOLID)) readback_prezero(hp.rb, host_table, region_words, 0, st, true);      // surface tables are sparse: zero-fill the host table meanwhile
 	if (tiles) {
 		const bool same = hp.mesh && memcmp(&hp.mesh_grid, grid, sizeof(*grid)) == 0 && hp.mesh_has_region == (region != nullptr) &&
 		                  (!region || memcmp(&hp.mesh_region, region, sizeof(*region)) == 0);
@@ -717,16 +713,62 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
 		if (rc) return rc;
 	}
 	CU(cudaEventRecord(hp.ev[2], st));
+	hp.last_tiles = tiles;
+	return VOXB200_OK;
+}
+// after the read-back has synchronised the stream: did the large-triangle queue overflow?
+static int host_indexed_check(Workspace* ws, HostPath& hp) {
 	unsigned long long overflow = 0ull;
-	if (!tiles) CU(cudaMemcpyAsync(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost, st));
-	rc = readback_table(hp.rb, hp.d_table, region_words, host_table, st, 0);
-	if (rc) return rc;
-	if (tiles) {
+	if (hp.last_tiles) {
 		uint64_t c[4];
-		if ((rc = voxb200_mesh_counters(hp.mesh, c))) return rc;
+		const int rc = voxb200_mesh_counters(hp.mesh, c);
+		if (rc) return rc;
 		overflow = c[1] == ~0ull;
+	} else {
+		CU(cudaMemcpy(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost));
 	}
 	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
+	return VOXB200_OK;
+}
+
+int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
+                                  unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]) {
+	const auto t_call = std::chrono::steady_clock::now();
+	if (!grid || !host_table || !host_verts || (!host_faces && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	HostPath& hp = g_hp[ws->device];
+	rc = ensure_host_path(hp);
+	if (rc) return rc;
+	ReadbackGuard guard{hp.rb};
+	size_t region_words = 0;
+	rc = host_indexed_to_device(grid, host_verts, n_verts, host_faces, host_table, flags, region, ws, hp, &region_words);
+	if (rc) return rc;
+	rc = readback_table(hp.rb, hp.d_table, region_words, host_table, hp.stream, 0);
+	if (rc) return rc;
+	if ((rc = host_indexed_check(ws, hp))) return rc;
+	return host_timing(hp, t_call, timing_ms);
+}
+
+int voxb200_voxelize_host_nonzero(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
+                                  unsigned int flags, const voxb200_region* region, const voxb200_word** words, size_t* n_words, float timing_ms[4]) {
+	const auto t_call = std::chrono::steady_clock::now();
+	if (!grid || !words || !n_words || !host_verts || (!host_faces && grid->n_triangles)) return fail(VOXB200_EINVAL, "NULL pointer");
+	Workspace* ws;
+	int rc = current_ws(&ws);
+	if (rc) return rc;
+	HostPath& hp = g_hp[ws->device];
+	rc = ensure_host_path(hp);
+	if (rc) return rc;
+	size_t region_words = 0;
+	rc = host_indexed_to_device(grid, host_verts, n_verts, host_faces, nullptr, flags, region, ws, hp, &region_words);
+	if (rc) return rc;
+	const void* pairs = nullptr;
+	rc = readback_pairs(hp.rb, hp.d_table, region_words, hp.stream, &pairs, n_words);
+	if (rc) return rc;
+	*words = static_cast<const voxb200_word*>(pairs);
+	if ((rc = host_indexed_check(ws, hp))) return rc;
 	return host_timing(hp, t_call, timing_ms);
 }
 

@@ -192,6 +192,7 @@ int readback_table(Readback& rb, const unsigned int* d_table, size_t words, unsi
 void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after, bool allow_early);
 void readback_cancel(Readback& rb);          // every exit of a call that started one (idempotent)
 struct ReadbackGuard { Readback& rb; ~ReadbackGuard() { readback_cancel(rb); } };
+int readback_pairs(Readback& rb, const unsigned int* d_table, size_t words, cudaStream_t st, const void** host_pairs, size_t* n_pairs);
 void readback_free(Readback& rb);
 int readback_default_threads();
 cudaError_t launch_bbox_reduce(const float* d_verts, size_t n_verts, float* d_minmax6, cudaStream_t st);

@@ -195,6 +195,17 @@ int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_ve
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]);
 
 /*
+ * The same call for a consumer that does not need the dense table: the table's NON-ZERO WORDS, ascending, as {index, bits} —
+ * index = word of the (region's) table, bits = its 32 voxels, MSB first (voxel 32*index + k is bit 31-k).  Everything a writer
+ * needs to walk the set voxels in table order, at 8 bytes per non-zero word over the link instead of the whole table (config 4:
+ * 56 MB instead of 1 GiB) and without the host writing G^3/8 bytes.  *words points into a pinned buffer owned by the library,
+ * valid until the next host entry point call on this device.  Tables of more than 2^32 words: voxelize in regions.
+ */
+typedef struct voxb200_word { uint32_t index; uint32_t bits; } voxb200_word;
+int voxb200_voxelize_host_nonzero(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
+                                  unsigned int flags, const voxb200_region* region, const voxb200_word** words, size_t* n_words, float timing_ms[4]);
+
+/*
  * The read-back alone: d_table (table_words words on the current device, 16-byte aligned for the sparse mode) -> host_table,
  * synchronous, after everything enqueued on `stream`.  info (when non-NULL): [0] 1 = the sparse mode ran, [1] non-zero words.
  * Replaces the reference's reliance on managed memory for the writers' G^3 checkVoxel reads (main.cpp:229-253, util.h:25-38).

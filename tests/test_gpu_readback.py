@@ -136,3 +136,21 @@ def test_host_entry_points_match_golden_through_the_readback(vb, golden, name, g
     out.fill_(-1)
     vb.voxelize_host_multi(grid, hv, hf, out, solid=bool(solid), n_devices=1)
     assert "%016x" % oracle.fnv1a64(out.numpy().view(np.uint32)) == want["fnv1a64"]
+
+
+@pytest.mark.parametrize("name,g,solid", [("bunny", 1024, 0), ("icosphere:64:128", 256, 0), ("bunny", 256, 1)])
+def test_host_nonzero_words_rebuild_the_golden_table(vb, golden, name, g, solid):
+    """voxb200_voxelize_host_nonzero: the {index, bits} pairs are exactly the non-zero words of the reference's table, ascending."""
+    want = golden[cases.case_key(name, g, solid, 0)]
+    v, f = cases.mesh(name)
+    grid = vb.grid_from_verts(v, g, len(f))
+    hv = torch.from_numpy(np.ascontiguousarray(v)).pin_memory()
+    hf = torch.from_numpy(np.ascontiguousarray(f)).pin_memory()
+    for _ in range(2):
+        pairs, ms = vb.voxelize_host_nonzero(grid, hv, hf, solid=bool(solid))
+    assert ms[3] > 0.0
+    assert np.all(pairs[:, 1] != 0) and np.all(np.diff(pairs[:, 0].astype(np.int64)) > 0)
+    table = np.zeros(vb.table_bytes(g) // 4, np.uint32)
+    table[pairs[:, 0]] = pairs[:, 1]
+    assert oracle.popcount(table) == want["popcount"]
+    assert "%016x" % oracle.fnv1a64(table) == want["fnv1a64"]
