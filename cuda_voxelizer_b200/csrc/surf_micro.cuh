@@ -20,6 +20,13 @@ __device__ __forceinline__ void red_or(unsigned int* p, unsigned int v) {
 __device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {       // mask = (mask << 1) | signbit(v)
 	return __funnelshift_l(__float_as_uint(v), mask, 1);
 }
+// "some edge function of the cell is negative" (cpu_voxelizer.cpp:145-159: three `< 0.0f` tests): the sign bit of a | b | c, one
+// LOP3 instead of two FMNMX on the half-rate ALU pipe.  Equal to testing each value: an edge value is a sum `... + d_e` whose last
+// term is never -0 (d_e itself ends in `+ max(0, .)`, and x + (+0) is never -0), so no value is -0; a NaN comes out of FADD as
+// the canonical 0x7fffffff, sign 0, and `NaN < 0` is false as well.
+__device__ __forceinline__ float any_negative3(float a, float b, float c) {
+	return __uint_as_float(__float_as_uint(a) | __float_as_uint(b) | __float_as_uint(c));
+}
 
 // The nine sums a[i] + b[j] of a 3x3 cell block in five additions (four of them FADD2), and one more level `+ d`
 // in five again: p[j] = cells (0,j),(1,j); q = cells (2,0),(2,1) (computed as b + a: IEEE addition commutes bit
@@ -93,7 +100,7 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 #pragma unroll
 		for (int j = 2; j >= 0; j--)
 #pragma unroll
-			for (int i = 0; i < 3; i++) rxy = sign_in(rxy, fminf(fminf(cell3(v[0], i, j), cell3(v[1], i, j)), cell3(v[2], i, j)));
+			for (int i = 0; i < 3; i++) rxy = sign_in(rxy, any_negative3(cell3(v[0], i, j), cell3(v[1], i, j), cell3(v[2], i, j)));
 	}
 	{
 		Cells3 v[3];                                // YZ cells (j,k): value = (n.x*p.y + n.y*p.z) + d; bit j + 3k, replicated over i
@@ -101,7 +108,7 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 #pragma unroll
 		for (int k = 2; k >= 0; k--)
 #pragma unroll
-			for (int j = 2; j >= 0; j--) ryz = sign_in(ryz, fminf(fminf(cell3(v[0], j, k), cell3(v[1], j, k)), cell3(v[2], j, k)));
+			for (int j = 2; j >= 0; j--) ryz = sign_in(ryz, any_negative3(cell3(v[0], j, k), cell3(v[1], j, k), cell3(v[2], j, k)));
 	}
 	{
 		Cells3 v[3];                                // ZX cells (k,i): value = (n.x*p.z + n.y*p.x) + d; bit i + 3k, replicated over j
@@ -109,7 +116,7 @@ __device__ __forceinline__ unsigned int surf_micro3(const SurfSetup& s, const Gr
 #pragma unroll
 		for (int k = 2; k >= 0; k--)
 #pragma unroll
-			for (int i = 0; i < 3; i++) rzx = sign_in(rzx, fminf(fminf(cell3(v[0], k, i), cell3(v[1], k, i)), cell3(v[2], k, i)));
+			for (int i = 0; i < 3; i++) rzx = sign_in(rzx, any_negative3(cell3(v[0], k, i), cell3(v[1], k, i), cell3(v[2], k, i)));
 	}
 	// expand the 9-bit cell masks to the 27-bit voxel layout b = (2-i) + 3j + 9k
 	const unsigned int xy27 = rxy * 0x40201u;                                           // copies at +0, +9, +18
@@ -185,7 +192,7 @@ __device__ __forceinline__ unsigned long long surf_micro4(const SurfSetup& s, co
 #pragma unroll
 		for (int j = 3; j >= 0; j--)
 #pragma unroll
-			for (int i = 0; i < 4; i++) rxy = sign_in(rxy, fminf(fminf(cell4(v[0], i, j), cell4(v[1], i, j)), cell4(v[2], i, j)));
+			for (int i = 0; i < 4; i++) rxy = sign_in(rxy, any_negative3(cell4(v[0], i, j), cell4(v[1], i, j), cell4(v[2], i, j)));
 	}
 	{
 		Cells4 v[3];
@@ -193,7 +200,7 @@ __device__ __forceinline__ unsigned long long surf_micro4(const SurfSetup& s, co
 #pragma unroll
 		for (int k = 3; k >= 0; k--)
 #pragma unroll
-			for (int j = 3; j >= 0; j--) ryz = sign_in(ryz, fminf(fminf(cell4(v[0], j, k), cell4(v[1], j, k)), cell4(v[2], j, k)));
+			for (int j = 3; j >= 0; j--) ryz = sign_in(ryz, any_negative3(cell4(v[0], j, k), cell4(v[1], j, k), cell4(v[2], j, k)));
 	}
 	{
 		Cells4 v[3];
@@ -201,7 +208,7 @@ __device__ __forceinline__ unsigned long long surf_micro4(const SurfSetup& s, co
 #pragma unroll
 		for (int k = 3; k >= 0; k--)
 #pragma unroll
-			for (int i = 0; i < 4; i++) rzx = sign_in(rzx, fminf(fminf(cell4(v[0], k, i), cell4(v[1], k, i)), cell4(v[2], k, i)));
+			for (int i = 0; i < 4; i++) rzx = sign_in(rzx, any_negative3(cell4(v[0], k, i), cell4(v[1], k, i), cell4(v[2], k, i)));
 	}
 	const int ex = s.x1 - s.x0, ey = s.y1 - s.y0, ez = s.z1 - s.z0;                      // 0..3
 	const unsigned int valid_xy = (((0xfu << (3 - ex)) & 0xfu) * 0x1111u) & ((16u << (4 * ey)) - 1u);
