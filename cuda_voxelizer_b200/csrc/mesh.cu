@@ -84,7 +84,7 @@ bool mesh_tileable(const GridParams& g, unsigned int flags) {
 namespace {
 
 // (Re)builds the handle's device state from a triangle source: a 9-float device soup, or device vertices + faces.
-int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const int* d_faces, cudaStream_t st) {
+int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const int* d_faces, size_t n_verts, cudaStream_t st) {
 	const GridParams& g = m.g;
 	const size_t n = (size_t)g.n_tris;
 	if (!m.tiles) {
@@ -96,7 +96,13 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 		float* tmp = nullptr;
 		if (sort) { CU(cudaMalloc(&tmp, (n * 9 + 16) * sizeof(float))); expanded = tmp; }
 		cudaError_t e = cudaSuccess;
-		if (d_faces) e = launch_expand_indexed(d_verts, d_faces, n, 0, false, expanded, st);
+		unsigned long long bad_faces = 0;
+		if (d_faces) {
+			if (!m.totals) CU(cudaMalloc(&m.totals, kPlanTotals * sizeof(unsigned long long)));
+			e = cudaMemsetAsync(m.totals, 0, kPlanTotals * sizeof(unsigned long long), st);
+			if (e == cudaSuccess) e = launch_expand_indexed(d_verts, d_faces, n, n_verts, false, expanded, st, m.totals + kPlanBadFaces);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(&bad_faces, m.totals + kPlanBadFaces, sizeof(bad_faces), cudaMemcpyDeviceToHost, st);
+		}
 		else if (n) e = cudaMemcpyAsync(expanded, d_soup, n * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st);
 		if (e == cudaSuccess && sort) {
 			size_t kc = m.keys_cap, hc = 0;
@@ -112,6 +118,7 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 		if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 		if (tmp) cudaFree(tmp);
 		if (e != cudaSuccess) return abi_fail_cuda(e, "voxb200_mesh prepare (direct schedule)");
+		if (bad_faces) return abi_fail(VOXB200_EINVAL, "%llu faces have a vertex index outside [0, %zu)", bad_faces, n_verts);
 		return VOXB200_OK;
 	}
 	// TILES
@@ -123,6 +130,7 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 	tg.G = g.G;
 	tg.ntx = g.G / tile_x; tg.nty = g.G / kTileY; tg.ntz = (g.rz1 - g.rz0) / kTileZ; tg.tz0 = g.rz0 / kTileZ;
 	tg.n_tiles = (unsigned int)tg.ntx * (unsigned int)tg.nty * (unsigned int)tg.ntz;
+	tg.n_verts = d_faces ? (unsigned int)(n_verts > 0x7fffffffull ? 0x7fffffffull : n_verts) : 0u;
 	const size_t nt = tg.n_tiles;
 	if (nt + 1 > m.tiles_cap || !m.cnt) {
 		for (unsigned int** p : {&m.cnt, &m.off, &m.order, &m.empty, &m.fill}) { if (*p) cudaFree(*p); *p = nullptr; }
@@ -143,6 +151,7 @@ int prepare(voxb200_mesh& m, const float* d_soup, const float* d_verts, const in
 	if (e == cudaSuccess) e = cudaMemcpyAsync(m.host_totals, m.totals, sizeof(m.host_totals), cudaMemcpyDeviceToHost, st);
 	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
 	if (e != cudaSuccess) return abi_fail_cuda(e, "voxb200_mesh prepare (count / plan)");
+	if (m.host_totals[kPlanBadFaces]) return abi_fail(VOXB200_EINVAL, "%llu faces have a vertex index outside [0, %zu)", m.host_totals[kPlanBadFaces], n_verts);
 	const unsigned long long inst = m.host_totals[kPlanInstances];
 	if (inst >= 0xfffffff0ull) return abi_fail(VOXB200_EINVAL, "more than 2^32 triangle instances in the tile plan");
 	const size_t side_max = (size_t)(m.host_totals[kPlanBigDirect] + m.host_totals[kPlanHeavyInstances]);
@@ -219,7 +228,7 @@ int voxb200_mesh_create(const voxb200_grid* grid, const float* d_tris9, unsigned
 	voxb200_mesh* m = nullptr;
 	int rc = create_common(grid, flags, region, &m);
 	if (rc) return rc;
-	rc = prepare(*m, d_tris9, nullptr, nullptr, (cudaStream_t)stream);
+	rc = prepare(*m, d_tris9, nullptr, nullptr, 0, (cudaStream_t)stream);
 	if (rc) { destroy(m); return rc; }
 	*out = m;
 	return VOXB200_OK;
@@ -231,7 +240,7 @@ int voxb200_mesh_create_indexed(const voxb200_grid* grid, const float* d_verts, 
 	voxb200_mesh* m = nullptr;
 	int rc = create_common(grid, flags, region, &m);
 	if (rc) return rc;
-	rc = prepare(*m, nullptr, d_verts, reinterpret_cast<const int*>(d_faces), (cudaStream_t)stream);
+	rc = prepare(*m, nullptr, d_verts, reinterpret_cast<const int*>(d_faces), n_verts, (cudaStream_t)stream);
 	if (rc) { destroy(m); return rc; }
 	*out = m;
 	return VOXB200_OK;
@@ -241,14 +250,14 @@ int voxb200_mesh_update(voxb200_mesh* m, const float* d_tris9, void* stream) {
 	if (!m || (!d_tris9 && m->g.n_tris)) return abi_fail(VOXB200_EINVAL, "NULL mesh / triangle pointer");
 	int rc = check_device(m);
 	if (rc) return rc;
-	return prepare(*m, d_tris9, nullptr, nullptr, (cudaStream_t)stream);
+	return prepare(*m, d_tris9, nullptr, nullptr, 0, (cudaStream_t)stream);
 }
 
 int voxb200_mesh_update_indexed(voxb200_mesh* m, const float* d_verts, size_t n_verts, const int32_t* d_faces, void* stream) {
 	if (!m || (m->g.n_tris && (!d_verts || !d_faces || n_verts == 0))) return abi_fail(VOXB200_EINVAL, "NULL mesh / vertex / face pointer");
 	int rc = check_device(m);
 	if (rc) return rc;
-	return prepare(*m, nullptr, d_verts, reinterpret_cast<const int*>(d_faces), (cudaStream_t)stream);
+	return prepare(*m, nullptr, d_verts, reinterpret_cast<const int*>(d_faces), n_verts, (cudaStream_t)stream);
 }
 
 int voxb200_mesh_voxelize(voxb200_mesh* m, unsigned int* d_table, unsigned int flags, void* stream) {

@@ -31,6 +31,7 @@ struct DevState {                       // persistent per device, grown on deman
 	int* d_faces = nullptr; size_t faces_bytes = 0;
 	float* d_tris = nullptr; size_t tris_bytes = 0;
 	unsigned int* d_table = nullptr; size_t table_bytes = 0;
+	unsigned long long* d_bad = nullptr;    // faces with an out-of-range vertex index (expansion of the non-tile schedules)
 	voxb200_mesh* mesh = nullptr;
 	voxb200_grid mesh_grid{}; voxb200_region mesh_region{}; size_t mesh_verts = 0;
 	cudaStream_t stream = nullptr;
@@ -175,7 +176,9 @@ void worker(Shared& S, int d) {
 		STEP(cudaEventRecord(D.ev[3], st));
 		STEP_RC(voxb200_mesh_voxelize(D.mesh, D.d_table, 0u, st));
 	} else {
-		STEP(launch_expand_indexed(D.d_verts, D.d_faces, n_faces, S.n_verts, false, D.d_tris, st));
+		if (!S.failed && !D.d_bad) STEP(cudaMalloc(&D.d_bad, sizeof(unsigned long long)));
+		STEP(cudaMemsetAsync(D.d_bad, 0, sizeof(unsigned long long), st));
+		STEP(launch_expand_indexed(D.d_verts, D.d_faces, n_faces, S.n_verts, false, D.d_tris, st, D.d_bad));
 		STEP(cudaEventRecord(D.ev[3], st));
 		if (solid) STEP_RC(voxb200_solid(S.grid, D.d_tris, D.d_table, S.flags & VOXB200_MORTON, region, st));
 		else STEP_RC(voxb200_surface(S.grid, D.d_tris, D.d_table, S.flags & VOXB200_MORTON, region, st));
@@ -193,6 +196,9 @@ void worker(Shared& S, int d) {
 		uint64_t c[4] = {0, 0, 0, 0};
 		const int rc = tiles ? voxb200_mesh_counters(D.mesh, c) : voxb200_last_counters(c);
 		if (rc == VOXB200_OK && c[1] == ~0ull) S.fail(VOXB200_EINVAL, "more than 2^32 (y,z) rows / sample blocks queued for the large-triangle path on one device: table contents undefined");
+		unsigned long long bad_faces = 0ull;
+		if (!tiles && D.d_bad && cudaMemcpy(&bad_faces, D.d_bad, sizeof(bad_faces), cudaMemcpyDeviceToHost) == cudaSuccess && bad_faces)
+			S.fail(VOXB200_EINVAL, "faces with a vertex index out of range: table contents undefined");
 	}
 	for (int k = 0; k < 4; k++) {
 		S.phase_ms[d][k] = 0.0f;
@@ -214,7 +220,7 @@ void multi_release_device(int dev) {
 	DevState& D = g_dev[dev];
 	if (D.mesh) voxb200_mesh_destroy(D.mesh);
 	readback_free(D.rb);
-	for (void* p : {(void*)D.d_verts, (void*)D.d_faces, (void*)D.d_tris, (void*)D.d_table}) if (p) cudaFree(p);
+	for (void* p : {(void*)D.d_verts, (void*)D.d_faces, (void*)D.d_tris, (void*)D.d_table, (void*)D.d_bad}) if (p) cudaFree(p);
 	if (D.stream) cudaStreamDestroy(D.stream);
 	for (auto& e : D.ev) if (e) cudaEventDestroy(e);
 	D = DevState();

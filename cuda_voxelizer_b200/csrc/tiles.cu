@@ -46,11 +46,18 @@ constexpr int kLptBins = 1024;
 // ------------------------------------------------------------------------------------------------
 // prepare
 // ------------------------------------------------------------------------------------------------
+// Returns false when a vertex index of the face lies outside [0, n_verts) (then clamped: nothing is read out of bounds; the count
+// kernel reports the face, voxb200_mesh_create_indexed fails).
 template <bool INDEXED>
-__device__ __forceinline__ void load_src_tri(const float* __restrict__ soup, const float* __restrict__ verts, const int* __restrict__ faces,
-                                             unsigned long long i, Tri& t) {
+__device__ __forceinline__ bool load_src_tri(const float* __restrict__ soup, const float* __restrict__ verts, const int* __restrict__ faces,
+                                             unsigned long long i, unsigned int n_verts, Tri& t) {
+	bool ok = true;
 	if (INDEXED) {
-		const int a = __ldg(faces + 3 * i), b = __ldg(faces + 3 * i + 1), c = __ldg(faces + 3 * i + 2);
+		int a = __ldg(faces + 3 * i), b = __ldg(faces + 3 * i + 1), c = __ldg(faces + 3 * i + 2);
+		if (n_verts && ((unsigned int)a >= n_verts || (unsigned int)b >= n_verts || (unsigned int)c >= n_verts)) {
+			ok = false;
+			a = min(max(a, 0), (int)n_verts - 1); b = min(max(b, 0), (int)n_verts - 1); c = min(max(c, 0), (int)n_verts - 1);
+		}
 		const float* pa = verts + 3 * (size_t)a;
 		const float* pb = verts + 3 * (size_t)b;
 		const float* pc = verts + 3 * (size_t)c;
@@ -60,6 +67,7 @@ __device__ __forceinline__ void load_src_tri(const float* __restrict__ soup, con
 	} else {
 		load_tri_aos(soup, i, t);
 	}
+	return ok;
 }
 
 __device__ __forceinline__ unsigned int tile_id(const TileGeom& tg, int tx, int ty, int tzl) {
@@ -84,9 +92,10 @@ __global__ void __launch_bounds__(kPrepBlock) tile_count_kernel(const GridParams
                                                                 unsigned long long* __restrict__ totals) {
 	const unsigned long long i = (unsigned long long)blockIdx.x * kPrepBlock + threadIdx.x;
 	unsigned int key = 0u;
+	bool bad = false;
 	if (i < g.n_tris) {
 		Tri t;
-		load_src_tri<INDEXED>(soup, verts, faces, i, t);
+		bad = !load_src_tri<INDEXED>(soup, verts, faces, i, tg.n_verts, t);
 		shift_tri(t, g);
 		SurfSetup s;
 		if (region_bbox(t, g, s)) {
@@ -119,6 +128,10 @@ __global__ void __launch_bounds__(kPrepBlock) tile_count_kernel(const GridParams
 	}
 	const unsigned int bigs = __ballot_sync(0xffffffffu, (key >> 30) == 2u);
 	if (bigs && (threadIdx.x & 31) == 0) atomicAdd(totals + kPlanBigDirect, (unsigned long long)__popc(bigs));
+	if (INDEXED) {
+		const unsigned int bads = __ballot_sync(0xffffffffu, bad);
+		if (bads && (threadIdx.x & 31) == 0) atomicAdd(totals + kPlanBadFaces, (unsigned long long)__popc(bads));
+	}
 	const unsigned int wides = __ballot_sync(0xffffffffu, (key >> 23) & 1u);
 	if (wides && (threadIdx.x & 31) == 0) atomicAdd(totals + kPlanWide, (unsigned long long)__popc(wides));
 }
@@ -234,7 +247,7 @@ __global__ void __launch_bounds__(kPrepBlock) tile_scatter_kernel(const GridPara
 	const unsigned int key = i < g.n_tris ? keys[i] : 0u;
 	const unsigned int kind = key >> 30;
 	Tri t;
-	if (kind) load_src_tri<INDEXED>(soup, verts, faces, i, t);
+	if (kind) load_src_tri<INDEXED>(soup, verts, faces, i, tg.n_verts, t);
 	bool to_side = kind == 2u;
 	const unsigned int act = __ballot_sync(0xffffffffu, kind == 1u);
 	if (kind == 1u) {

@@ -18,11 +18,20 @@ __global__ void __launch_bounds__(kUpBlock) soup_to_soa4_kernel(const float* __r
 }
 
 template <bool SOA4>
+// Face indices outside [0, n_verts) are counted into *bad (the caller reports them) and clamped, so nothing is read out of bounds.
 __global__ void __launch_bounds__(kUpBlock) expand_indexed_kernel(const float* __restrict__ verts, const int* __restrict__ faces,
-                                                                  size_t n_faces, float* __restrict__ out) {
+                                                                  size_t n_faces, unsigned int n_verts, unsigned long long* __restrict__ bad,
+                                                                  float* __restrict__ out) {
 	const size_t i = (size_t)blockIdx.x * kUpBlock + threadIdx.x;
 	if (i >= n_faces) return;
-	const int a = __ldg(faces + 3 * i), b = __ldg(faces + 3 * i + 1), c = __ldg(faces + 3 * i + 2);
+	int a = __ldg(faces + 3 * i), b = __ldg(faces + 3 * i + 1), c = __ldg(faces + 3 * i + 2);
+	if (n_verts) {
+		const bool oob = (unsigned int)a >= n_verts || (unsigned int)b >= n_verts || (unsigned int)c >= n_verts;
+		if (oob) {
+			if (bad) atomicAdd(bad, 1ull);
+			a = min(max(a, 0), (int)n_verts - 1); b = min(max(b, 0), (int)n_verts - 1); c = min(max(c, 0), (int)n_verts - 1);
+		}
+	}
 	const float* pa = verts + 3 * (size_t)a;
 	const float* pb = verts + 3 * (size_t)b;
 	const float* pc = verts + 3 * (size_t)c;
@@ -281,11 +290,13 @@ cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tri
 	return cudaGetLastError();
 }
 
-cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t, bool soa4, float* d_out, cudaStream_t st) {
+cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t n_verts,
+                                  bool soa4, float* d_out, cudaStream_t st, unsigned long long* d_bad) {
 	if (n_faces == 0) return cudaSuccess;
 	const unsigned blocks = (unsigned)((n_faces + kUpBlock - 1) / kUpBlock);
-	if (soa4) expand_indexed_kernel<true><<<blocks, kUpBlock, 0, st>>>(d_verts, d_faces, n_faces, d_out);
-	else expand_indexed_kernel<false><<<blocks, kUpBlock, 0, st>>>(d_verts, d_faces, n_faces, d_out);
+	const unsigned int nv = n_verts > 0x7fffffffull ? 0x7fffffffu : (unsigned int)n_verts;       // 0: the caller vouches for the indices
+	if (soa4) expand_indexed_kernel<true><<<blocks, kUpBlock, 0, st>>>(d_verts, d_faces, n_faces, nv, d_bad, d_out);
+	else expand_indexed_kernel<false><<<blocks, kUpBlock, 0, st>>>(d_verts, d_faces, n_faces, nv, d_bad, d_out);
 	g_launch_count++;
 	return cudaGetLastError();
 }

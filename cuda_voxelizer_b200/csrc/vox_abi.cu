@@ -34,6 +34,7 @@ struct HostPath {
 	int next_buf = 0;
 	Readback rb;                            // device table -> host table (readback.cu)
 	bool last_tiles = false;                // the last indexed host call took the tile schedule
+	unsigned long long* d_bad = nullptr;    // faces with an out-of-range vertex index seen by the expansion of the last indexed host call
 };
 HostPath g_hp[kMaxDevices];
 
@@ -480,19 +481,22 @@ int voxb200_upload_indexed(const float* host_verts, size_t n_verts, const int32_
 	HostPath& hp = g_hp[ws->device];
 	rc = ensure_host_path(hp);
 	if (rc) return rc;
-	for (size_t i = 0; i < n_faces * 3; i++)
-		if (host_faces[i] < 0 || (size_t)host_faces[i] >= n_verts) return fail(VOXB200_EINVAL, "face index %d out of range at %zu", host_faces[i], i);
+	// (face indices are range-checked on the device while they are expanded: counted, clamped, reported below)
 	cudaStream_t st = (cudaStream_t)stream;
 	float* d_verts = nullptr; int* d_faces = nullptr; float* d_out = nullptr; float* d_mm = nullptr;
+	unsigned long long bad_faces = 0;
 	cudaError_t e = cudaMalloc(&d_verts, n_verts * 3 * sizeof(float));
 	if (e == cudaSuccess) e = cudaMalloc(&d_faces, n_faces ? n_faces * 3 * sizeof(int) : 16);
 	if (e == cudaSuccess) e = cudaMalloc(&d_out, n_faces ? n_faces * (soa4 ? 12 : 9) * sizeof(float) : 16);
-	if (e == cudaSuccess) e = cudaMalloc(&d_mm, 6 * sizeof(float));
+	if (e == cudaSuccess) e = cudaMalloc(&d_mm, 8 * sizeof(float));          // 6 floats of bbox + the bad-face counter
 	if (e == cudaSuccess) {
+		unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(d_mm + 6);
+		e = cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), st);
 		rc = h2d(hp, d_verts, host_verts, n_verts * 3 * sizeof(float), st);
 		if (!rc) rc = h2d(hp, d_faces, host_faces, n_faces * 3 * sizeof(int), st);
-		if (!rc) {
-			e = launch_expand_indexed(d_verts, d_faces, n_faces, n_verts, soa4 != 0, d_out, st);
+		if (!rc && e == cudaSuccess) {
+			e = launch_expand_indexed(d_verts, d_faces, n_faces, n_verts, soa4 != 0, d_out, st, d_bad);
+			if (e == cudaSuccess) e = cudaMemcpyAsync(&bad_faces, d_bad, sizeof(bad_faces), cudaMemcpyDeviceToHost, st);
 			if (e == cudaSuccess && mesh_min && mesh_max) {
 				e = launch_bbox_reduce(d_verts, n_verts, d_mm, st);
 				float mm[6];
@@ -506,6 +510,7 @@ int voxb200_upload_indexed(const float* host_verts, size_t n_verts, const int32_
 	cudaFree(d_verts); cudaFree(d_faces); cudaFree(d_mm);
 	if (rc) { cudaFree(d_out); return rc; }
 	if (e != cudaSuccess) { cudaFree(d_out); return fail_cuda(e, "voxb200_upload_indexed"); }
+	if (bad_faces) { cudaFree(d_out); return fail(VOXB200_EINVAL, "%llu faces have a vertex index out of range [0, %zu)", bad_faces, n_verts); }
 	*d_tris = d_out;
 	return VOXB200_OK;
 }
@@ -706,7 +711,9 @@ static int host_indexed_to_device(const voxb200_grid* grid, const float* host_ve
 		rc = voxb200_mesh_voxelize(hp.mesh, hp.d_table, 0u, st);
 		if (rc) return rc;
 	} else {
-		cudaError_t e = launch_expand_indexed(hp.d_verts, hp.d_faces, n_faces, n_verts, false, hp.d_tris, st);
+		if (!hp.d_bad) CU(cudaMalloc(&hp.d_bad, sizeof(unsigned long long)));
+		CU(cudaMemsetAsync(hp.d_bad, 0, sizeof(unsigned long long), st));
+		cudaError_t e = launch_expand_indexed(hp.d_verts, hp.d_faces, n_faces, n_verts, false, hp.d_tris, st, hp.d_bad);
 		if (e != cudaSuccess) return fail_cuda(e, "expand_indexed");
 		CU(cudaEventRecord(hp.ev[1], st));
 		rc = run_path((flags & VOXB200_SOLID) != 0, grid, hp.d_tris, hp.d_table, flags & VOXB200_MORTON, region, st);
@@ -726,6 +733,9 @@ static int host_indexed_check(Workspace* ws, HostPath& hp) {
 		overflow = c[1] == ~0ull;
 	} else {
 		CU(cudaMemcpy(&overflow, ws->counters + kCtrQueueOverflow, sizeof(overflow), cudaMemcpyDeviceToHost));
+		unsigned long long bad_faces = 0ull;
+		if (hp.d_bad) CU(cudaMemcpy(&bad_faces, hp.d_bad, sizeof(bad_faces), cudaMemcpyDeviceToHost));
+		if (bad_faces) return fail(VOXB200_EINVAL, "%llu faces have a vertex index out of range: table contents undefined", bad_faces);
 	}
 	if (overflow) return fail(VOXB200_EINVAL, "the mesh queues more than 2^32 (y,z) rows / sample blocks for the large-triangle path at this grid size: table contents undefined");
 	return VOXB200_OK;
@@ -831,7 +841,7 @@ int voxb200_release(void) {
 	readback_free(hp.rb);
 	multi_release_device(dev);
 	void* dev_ptrs[] = {ws.counters, ws.queue, ws.setups, ws.dir, ws.route_masks, ws.route_counts, ws.scratch, ws.row_count, ws.row_marks,
-	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces};
+	                    hp.d_tris, hp.d_table, hp.d_verts, hp.d_faces, hp.d_bad};
 	for (void* p : dev_ptrs) if (p) cudaFree(p);
 	for (void* p : hp.pinned) if (p) cudaFreeHost(p);
 	if (ws.prof_ev) {

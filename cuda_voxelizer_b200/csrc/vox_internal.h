@@ -88,7 +88,7 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g, const float* d_tris
 // Upload helpers (main.cpp:61-80 replaced)
 cudaError_t launch_soup_to_soa4(const float* d_soup, float* d_soa4, size_t n_tris, cudaStream_t st);
 cudaError_t launch_expand_indexed(const float* d_verts, const int* d_faces, size_t n_faces, size_t n_verts,
-                                  bool soa4, float* d_out, cudaStream_t st);
+                                  bool soa4, float* d_out, cudaStream_t st, unsigned long long* d_bad = nullptr);      // n_verts != 0: indices outside [0, n_verts) are clamped and counted into *d_bad
 // Upload-path layer sort: d_out = d_soup ordered by the z-layer of each triangle's lowest vertex (d_keys: n_tris words, d_hist: G words of scratch)
 cudaError_t launch_layer_sort(const GridParams& g, const float* d_soup, float* d_out, unsigned int* d_keys, unsigned int* d_hist, cudaStream_t st);
 cudaError_t launch_route(const GridParams& g, bool solid, const float* d_soup, float* d_out, unsigned long long* d_cursor, cudaStream_t st);
@@ -115,6 +115,7 @@ struct TileGeom {
 	int G;
 	int tz0;                        // first tile layer of the region (region z0 / kTileZ)
 	unsigned int n_tiles;
+	unsigned int n_verts;           // indexed input: vertices (0: not known, indices are trusted)
 };
 enum PlanTotal {                    // device-side totals of the planning pass (u64 each)
 	kPlanInstances = 0,             // (triangle, tile) records
@@ -124,7 +125,8 @@ enum PlanTotal {                    // device-side totals of the planning pass (
 	kPlanHeavyInstances = 5,        // instances that fell into over-full tiles (they take the side path)
 	kPlanSideFill = 6,              // triangles written to the side soup
 	kPlanWide = 7,                  // small triangles that need the 64-candidate evaluation
-	kPlanTotals = 8
+	kPlanBadFaces = 8,              // faces with a vertex index outside [0, n_verts) (indexed input; they are clamped and reported)
+	kPlanTotals = 9
 };
 struct TilePlan {
 	TileGeom geom;

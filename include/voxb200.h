@@ -189,7 +189,8 @@ int voxb200_voxelize_host(const voxb200_grid* grid, const float* host_tris9, uns
 /*
  * Same, from the INDEXED mesh the caller holds (what the reference's main() has after TriMesh::read): uploads
  * 12 B/vertex + 12 B/face instead of the 36 B/triangle soup and expands on the GPU (main.cpp:61-80 replaced).
- * Face indices are NOT range-checked here (voxb200_upload_indexed does check).  grid->n_triangles = number of faces.
+ * Face indices are range-checked on the device (out-of-range ones are clamped, counted, and fail the call with VOXB200_EINVAL).
+ * grid->n_triangles = number of faces.
  */
 int voxb200_voxelize_host_indexed(const voxb200_grid* grid, const float* host_verts, size_t n_verts, const int32_t* host_faces,
                                   unsigned int* host_table, unsigned int flags, const voxb200_region* region, float timing_ms[4]);

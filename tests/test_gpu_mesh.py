@@ -226,3 +226,31 @@ def test_mesh_rejects_bad_arguments(vb):
     with pytest.raises(vb.VoxError):
         vb.Mesh(bad, tris=d_tris)
     m.close()
+
+
+def test_out_of_range_face_indices_are_reported_not_read(vb):
+    """Indexed input with a vertex index outside [0, n_verts): every entry point that takes faces fails with EINVAL (the indices are
+    checked on the device while they are consumed, and clamped so that nothing is read out of bounds) and works again afterwards."""
+    import torch
+    v, f = cases.mesh("icosphere:64:128")
+    g = 256
+    grid = vb.grid_from_verts(v, g, len(f))
+    good = vb.voxelize_host_indexed(grid, v, f)[0].copy()
+    for bad_value in (len(v), -1, 2**31 - 1):
+        fb = f.copy()
+        fb[len(fb) // 2, 1] = bad_value
+        with pytest.raises(vb.VoxError):
+            vb.voxelize_host_indexed(grid, v, fb)                     # tile schedule
+        with pytest.raises(vb.VoxError):
+            vb.voxelize_host_indexed(grid, v, fb, solid=True)         # expansion + one-shot kernels
+        with pytest.raises(vb.VoxError):
+            vb.upload_indexed(v, fb)
+        with pytest.raises(vb.VoxError):
+            vb.Mesh(grid, verts=torch.from_numpy(np.ascontiguousarray(v)).cuda(), faces=torch.from_numpy(np.ascontiguousarray(fb)).cuda())
+        with pytest.raises(vb.VoxError):
+            vb.Mesh(grid, verts=torch.from_numpy(np.ascontiguousarray(v)).cuda(), faces=torch.from_numpy(np.ascontiguousarray(fb)).cuda(), solid=True)
+        with pytest.raises(vb.VoxError):
+            vb.voxelize_host_multi(grid, np.ascontiguousarray(v), np.ascontiguousarray(fb), n_devices=1)
+        with pytest.raises(vb.VoxError):
+            vb.voxelize_host_multi(grid, np.ascontiguousarray(v), np.ascontiguousarray(fb), solid=True, n_devices=1)
+    assert np.array_equal(vb.voxelize_host_indexed(grid, v, f)[0], good)
