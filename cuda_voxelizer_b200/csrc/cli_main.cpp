@@ -125,6 +125,7 @@ int main(int argc, char* argv[]) {
 	voxb200_grid grid;
 	int rc = voxb200_make_grid(mesh.bbox_min, mesh.bbox_max, opt.gridsize, mesh.n_faces(), &grid);
 	if (rc) die_abi("voxb200_make_grid", rc);
+	static_assert(sizeof(voxinfo) == sizeof(voxb200_grid), "voxinfo / voxb200_grid layout");      // byte-identical (static_asserts in dropin.cu)
 	const voxinfo& info = *reinterpret_cast<const voxinfo*>(&grid);
 	printf("[Voxelization] Bounding Box: (%f,%f,%f)-(%f,%f,%f) \n", info.bbox.min.x, info.bbox.min.y, info.bbox.min.z, info.bbox.max.x, info.bbox.max.y, info.bbox.max.z);
 	printf("[Voxelization] Grid size: %i %i %i \n", info.gridsize.x, info.gridsize.y, info.gridsize.z);
@@ -196,7 +197,7 @@ int main(int argc, char* argv[]) {
 
 	// -o morton dumps the raw table (util_io.cpp:192-200).  Every other writer only needs the SET voxels: they are
 	// compacted on the GPU and only that list crosses PCIe.
-	std::vector<unsigned int> vtable;
+	unsigned int* table_host = nullptr;
 	VoxelList voxels;
 	voxels.gridsize = opt.gridsize;
 	const double t_rb = now_ms();
@@ -204,9 +205,13 @@ int main(int argc, char* argv[]) {
 	std::vector<unsigned char> rle;
 	const bool device_rle = opt.format == Format::binvox && opt.gridsize >= 256 && opt.gridsize % 256 == 0 && opt.gridsize <= 4096;
 	if (morton) {
-		vtable.resize(vtable_size / 4);
-		rc = voxb200_memcpy_d2h(vtable.data(), d_table, vtable_size, nullptr);
-		if (rc) die_abi("voxb200_memcpy_d2h", rc);
+		// the raw table: a dense copy, or (large, mostly empty tables into aligned memory) its non-zero words expanded by host threads
+		rc = voxb200_host_alloc(reinterpret_cast<void**>(&table_host), vtable_size);      // pinned and page-aligned
+		if (rc) die_abi("voxb200_host_alloc", rc);
+		uint64_t info[2] = {0, 0};
+		rc = voxb200_download_table(d_table, vtable_size / 4, table_host, nullptr, info);
+		if (rc) die_abi("voxb200_download_table", rc);
+		if (info[0]) printf("[Voxel Grid] read back as %llu non-zero words \n", (unsigned long long)info[1]);
 	} else if (device_rle) {
 		unsigned char* d_rle = nullptr;
 		size_t n_rle = 0;
@@ -239,7 +244,7 @@ int main(int argc, char* argv[]) {
 	printf("\n## FILE OUTPUT \n");
 	const double t_out = now_ms();
 	switch (opt.format) {
-		case Format::morton: write_binary(vtable.data(), vtable_size, opt.filename); break;
+		case Format::morton: write_binary(table_host, vtable_size, opt.filename); break;
 		case Format::binvox: if (device_rle) write_binvox_payload(rle.data(), rle.size(), info, opt.filename); else write_binvox(voxels, info, opt.filename); break;
 		case Format::obj_points: write_obj_pointcloud(voxels, info, opt.filename); break;
 		case Format::obj_cubes: write_obj_cubes(voxels, info, opt.filename); break;
