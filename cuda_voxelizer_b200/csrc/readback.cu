@@ -92,9 +92,10 @@ void readback_free(Readback& rb) {
 	if (rb.d_pairs) cudaFree(rb.d_pairs);
 	if (rb.h_offsets) cudaFreeHost(rb.h_offsets);
 	if (rb.h_pairs) cudaFreeHost(rb.h_pairs);
+	if (rb.host) delete_host(rb.host);              // first: its workers may still be polling go_ev
 	for (int k = 0; k < rb.n_ev; k++) cudaEventDestroy(rb.ev[k]);
 	delete[] rb.ev;
-	if (rb.host) delete_host(rb.host);
+	if (rb.go_ev) cudaEventDestroy(rb.go_ev);
 	rb = Readback();
 	cudaGetLastError();
 }
@@ -202,7 +203,6 @@ static void settle_prezero(ReadbackHost& H) {
 // `after`: the stream position behind which the zero-fill may start — behind the upload's host-to-device copies, because the
 // streaming stores and the copy engine's reads of host memory slow each other down (measured: a 3.3 ms upload took 7.1 ms next
 // to eight zero-filling threads, and the whole call got slower); nullptr... is not a stream here: pass the stream the copies are on.
-static void CUDART_CB prezero_go(void* flag) { static_cast<std::atomic<bool>*>(flag)->store(true); }
 
 void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after, bool allow_early) {
 	static const bool off = getenv("VOXB200_NO_PREZERO") != nullptr;
@@ -215,12 +215,24 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 	H.table = host_table; H.words = words; H.n_slices = slices_for(blocks);
 	H.zeroed.assign((size_t)H.n_slices, 0);
 	H.next = 0; H.cancel = false; H.go = false; H.active = true;
+	// "the stream is past the upload": an event the waiting workers poll (a host function in the stream would do, but its callback
+	// thread wakes up late every now and then and everything enqueued behind it waits: measured as 30 ms outliers on 1 ms calls)
+	int dev = -1;
+	if (!rb.go_ev && cudaEventCreateWithFlags(&rb.go_ev, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); rb.go_ev = nullptr; }
+	if (!rb.go_ev || cudaEventRecord(rb.go_ev, after) != cudaSuccess || cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); H.go = true; }
+	cudaEvent_t go_ev = rb.go_ev;
 	ReadbackHost* h = &H;
 	// a few workers start at once (a gentle stream of stores costs the upload little), the rest when the upload is through
 	static const int early_default = [] { const char* e = getenv("VOXB200_PREZERO_EARLY"); const int v = e ? atoi(e) : 2; return v < 0 ? 0 : v; }();
 	const int early = allow_early ? early_default : 0;      // (several devices upload at once: every early worker is one too many, measured)
-	H.pool.submit([h, blocks, early](int w) {
-		while (w >= early && !h->go.load() && !h->cancel.load()) std::this_thread::sleep_for(std::chrono::microseconds(20));
+	H.pool.submit([h, blocks, early, go_ev, dev](int w) {
+		if (w >= early && !h->go.load()) {
+			if (dev >= 0) cudaSetDevice(dev);
+			while (!h->go.load() && !h->cancel.load()) {
+				if (cudaEventQuery(go_ev) != cudaErrorNotReady) { cudaGetLastError(); h->go = true; break; }
+				std::this_thread::sleep_for(std::chrono::microseconds(20));
+			}
+		}
 		for (;;) {
 			if (h->cancel.load()) break;
 			const int s = h->next.fetch_add(1);
@@ -232,7 +244,6 @@ void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int 
 			h->zeroed[(size_t)s] = 1;
 		}
 	});
-	if (cudaLaunchHostFunc(after, prezero_go, &H.go) != cudaSuccess) { cudaGetLastError(); H.go = true; }
 }
 
 // The non-zero words alone: ascending {word index, value} pairs in the Readback's pinned host buffer (valid until its next call).

@@ -183,6 +183,7 @@ struct Readback {
 	void* d_pairs = nullptr; size_t pairs_cap = 0;                          // pairs
 	void* h_pairs = nullptr; size_t h_pairs_cap = 0;                        // pinned
 	cudaEvent_t* ev = nullptr; int n_ev = 0;
+	cudaEvent_t go_ev = nullptr;            // recorded behind the upload: the zero-fill workers that wait for it poll it
 	void* host = nullptr;                   // host threads + the zero-fill that runs ahead (readback.cu)
 	// what the last call did
 	int last_mode = 0;                      // 0 dense copy, 1 sparse
