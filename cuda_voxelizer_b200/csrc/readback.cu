@@ -170,7 +170,7 @@ struct ReadbackHost {
 	int n_slices = 0;
 	std::atomic<int> next{0};
 	std::atomic<bool> cancel{false};
-	std::atomic<bool> go{false};             // set from the stream (cudaLaunchHostFunc) once the upload has left host memory alone
+	std::atomic<bool> go{false};             // the stream is past the upload (a polling worker saw go_ev fire, or the read-back has begun)
 	std::vector<unsigned char> zeroed;       // per slice; a worker sets its slices' flags before it returns
 };
 
@@ -200,10 +200,10 @@ static void settle_prezero(ReadbackHost& H) {
 // A host entry point that expects a sparse table calls this before its first copy: the workers start streaming zeros over the host
 // table while the GPU is still busy with the upload and the voxelization; the read-back then only writes the lines that hold
 // non-zero words (and finishes whatever part of the zero-fill was still to do in the same pass as those lines).
-// `after`: the stream position behind which the zero-fill may start — behind the upload's host-to-device copies, because the
-// streaming stores and the copy engine's reads of host memory slow each other down (measured: a 3.3 ms upload took 7.1 ms next
-// to eight zero-filling threads, and the whole call got slower); nullptr... is not a stream here: pass the stream the copies are on.
-
+// `after`: the stream the upload's host-to-device copies were enqueued on.  Most workers only start once the stream is past the
+// point it is at now, because streaming stores and the copy engine's reads of host memory slow each other down (measured: a
+// 3.3 ms upload took 7.1 ms next to eight zero-filling threads, and the whole call got slower); `allow_early` lets two of them
+// start at once (measured: the upload does not notice two).
 void readback_prezero(Readback& rb, unsigned int* host_table, size_t words, int host_threads, cudaStream_t after, bool allow_early) {
 	static const bool off = getenv("VOXB200_NO_PREZERO") != nullptr;
 	if (off || !sparse_eligible(nullptr, words, host_table)) return;
