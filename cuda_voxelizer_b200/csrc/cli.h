@@ -19,7 +19,8 @@ struct Mesh {
 	size_t n_faces() const { return faces.size() / 3; }
 };
 
-// OBJ ("v", "f" with a, a/t, a//n, a/t/n; polygons fanned; negative indices) and ASCII/binary-little-endian PLY.
+// OBJ ("v", "f" with a, a/t, a//n, a/t/n; negative indices), PLY (ASCII, binary little- / big-endian, triangle strips), OFF,
+// STL (binary / ASCII) and 3DS; polygons through trimesh2's tess() rule (quads along the shorter diagonal).
 bool load_mesh(const std::string& path, Mesh& mesh, std::string& error);
 
 // The reader side of the table layout (util.h:25-38).

@@ -482,6 +482,144 @@ bool load_ply(const std::string& path, Mesh& m, std::string& error) {
 	return true;
 }
 
+// ---- OFF, STL, 3DS ------------------------------------------------------------------------------
+// The other formats the reference's help text names or trimesh2 reads for it (main.cpp:121 ".ply, .obj, .3ds"): small, serial
+// readers over the mapped file.  OFF: "OFF", counts, vertices, polygons (through tess()).  STL: binary (80-byte header, count,
+// 50-byte records) or ASCII ("vertex x y z" lines); three fresh vertices per facet, as trimesh2 reads it (no welding).
+// 3DS: chunk tree 0x4D4D > 0x3D3D > 0x4000 (named object) > 0x4100 (mesh) > 0x4110 vertices / 0x4120 faces; objects are appended
+// with their vertex offsets.
+struct Mapped {
+	const char* base = nullptr; size_t size = 0;
+	bool open_file(const std::string& path, std::string& error) {
+		const int fd = open(path.c_str(), O_RDONLY);
+		if (fd < 0) { error = "cannot open " + path; return false; }
+		struct stat st;
+		if (fstat(fd, &st) != 0 || st.st_size == 0) { close(fd); error = "empty file " + path; return false; }
+		size = (size_t)st.st_size;
+		void* map = mmap(nullptr, size, PROT_READ, MAP_PRIVATE, fd, 0);
+		close(fd);
+		if (map == MAP_FAILED) { error = "cannot map " + path; return false; }
+		base = static_cast<const char*>(map);
+		return true;
+	}
+	~Mapped() { if (base) munmap(const_cast<char*>(base), size); }
+};
+
+// next whitespace-separated token on [p, end), skipping '#' comments to the end of their line; false at the end
+bool next_token(const char*& p, const char* end, const char*& tok, const char*& tok_end) {
+	for (;;) {
+		while (p < end && (is_blank(*p) || is_eol(*p))) p++;
+		if (p < end && *p == '#') { while (p < end && *p != '\n') p++; continue; }
+		break;
+	}
+	if (p >= end) return false;
+	tok = p;
+	while (p < end && !is_blank(*p) && !is_eol(*p)) p++;
+	tok_end = p;
+	return true;
+}
+
+bool load_off(const std::string& path, Mesh& m, std::string& error) {
+	Mapped f;
+	if (!f.open_file(path, error)) return false;
+	const char* p = f.base; const char* end = f.base + f.size;
+	const char *t, *te;
+	if (!next_token(p, end, t, te)) { error = "empty OFF file"; return false; }
+	// the "OFF" keyword may be missing, or be followed by the counts on the same line
+	if (!(te - t >= 3 && (memcmp(te - 3, "OFF", 3) == 0))) p = t;
+	long counts[3] = {0, 0, 0};
+	for (int k = 0; k < 3; k++) {
+		if (!next_token(p, end, t, te)) { error = "OFF header is incomplete"; return false; }
+		const char* q = t; counts[k] = parse_long(q, te);
+	}
+	if (counts[0] <= 0 || counts[1] < 0) { error = "OFF header has no vertices"; return false; }
+	m.vertices.resize((size_t)counts[0] * 3);
+	for (size_t i = 0; i < m.vertices.size(); i++) {
+		if (!next_token(p, end, t, te)) { error = "OFF file ends inside the vertices"; return false; }
+		const char* q = t; m.vertices[i] = parse_float(q, te);
+	}
+	std::vector<int32_t> poly;
+	for (long i = 0; i < counts[1]; i++) {
+		if (!next_token(p, end, t, te)) { error = "OFF file ends inside the faces"; return false; }
+		const char* q = t; const long n = parse_long(q, te);
+		poly.clear();
+		for (long k = 0; k < n; k++) {
+			if (!next_token(p, end, t, te)) { error = "OFF file ends inside the faces"; return false; }
+			q = t; poly.push_back((int32_t)parse_long(q, te));
+		}
+		tess(m.vertices, poly, m.faces);
+		while (p < end && !is_eol(*p)) p++;            // colours behind the indices
+	}
+	return true;
+}
+
+bool load_stl(const std::string& path, Mesh& m, std::string& error) {
+	Mapped f;
+	if (!f.open_file(path, error)) return false;
+	// binary when the size matches the record count (ASCII files start with "solid", but so do some binary ones)
+	if (f.size >= 84) {
+		uint32_t n = 0;
+		memcpy(&n, f.base + 80, 4);
+		if (f.size == 84 + (size_t)n * 50) {
+			m.vertices.resize((size_t)n * 9);
+			m.faces.resize((size_t)n * 3);
+			for (size_t i = 0; i < n; i++) {
+				memcpy(m.vertices.data() + 9 * i, f.base + 84 + 50 * i + 12, 36);
+				for (int k = 0; k < 3; k++) m.faces[3 * i + k] = (int32_t)(3 * i + k);
+			}
+			return true;
+		}
+	}
+	const char* p = f.base; const char* end = f.base + f.size;
+	const char *t, *te;
+	while (next_token(p, end, t, te)) {
+		if (te - t == 6 && memcmp(t, "vertex", 6) == 0)
+			for (int k = 0; k < 3; k++) {
+				if (!next_token(p, end, t, te)) { error = "STL file ends inside a vertex"; return false; }
+				const char* q = t; m.vertices.push_back(parse_float(q, te));
+			}
+	}
+	const size_t nv = m.vertices.size() / 3;
+	if (nv == 0 || nv % 3 != 0) { error = "not an STL file (no facets found)"; return false; }
+	m.faces.resize(nv);
+	for (size_t i = 0; i < nv; i++) m.faces[i] = (int32_t)i;
+	return true;
+}
+
+bool load_3ds(const std::string& path, Mesh& m, std::string& error) {
+	Mapped f;
+	if (!f.open_file(path, error)) return false;
+	const unsigned char* b = reinterpret_cast<const unsigned char*>(f.base);
+	auto u16 = [&](size_t at) { return (unsigned)(b[at] | (b[at + 1] << 8)); };
+	auto u32 = [&](size_t at) { return (size_t)b[at] | ((size_t)b[at + 1] << 8) | ((size_t)b[at + 2] << 16) | ((size_t)b[at + 3] << 24); };
+	if (f.size < 6 || u16(0) != 0x4D4D) { error = "not a 3DS file"; return false; }
+	size_t vertex_base = 0;
+	// iterative walk: container chunks are entered, everything else is skipped by its length
+	size_t at = 0;
+	while (at + 6 <= f.size) {
+		const unsigned id = u16(at);
+		const size_t len = u32(at + 2);
+		if (len < 6 || at + len > f.size) { error = "3DS chunk runs past the end of the file"; return false; }
+		if (id == 0x4D4D || id == 0x3D3D || id == 0x4100) { at += 6; continue; }                    // main, editor, triangle mesh: descend
+		if (id == 0x4000) { size_t q = at + 6; while (q < at + len && b[q]) q++; at = q + 1; continue; }   // object: skip its name, descend
+		if (id == 0x4110) {
+			const size_t n = u16(at + 6);
+			if (8 + n * 12 > len) { error = "3DS vertex list is truncated"; return false; }
+			vertex_base = m.vertices.size() / 3;
+			const size_t old = m.vertices.size();
+			m.vertices.resize(old + n * 3);
+			memcpy(m.vertices.data() + old, b + at + 8, n * 12);
+		} else if (id == 0x4120) {
+			const size_t n = u16(at + 6);
+			if (8 + n * 8 > len) { error = "3DS face list is truncated"; return false; }
+			for (size_t i = 0; i < n; i++)
+				for (int k = 0; k < 3; k++) m.faces.push_back((int32_t)(vertex_base + u16(at + 8 + 8 * i + 2 * k)));
+		}
+		at += len;
+	}
+	return true;
+}
+
 }  // namespace
 
 bool load_mesh(const std::string& path, Mesh& m, std::string& error) {
@@ -493,7 +631,10 @@ bool load_mesh(const std::string& path, Mesh& m, std::string& error) {
 	const char* serial = getenv("VOXCLI_SERIAL_LOADER");
 	if (ext == "obj") ok = (serial && serial[0] == '1') ? load_obj(path, m, error) : load_obj_parallel(path, m, error);
 	else if (ext == "ply") ok = load_ply(path, m, error);
-	else { error = "unsupported mesh format ." + ext + " (this build reads .obj and .ply; trimesh2 is not linked)"; return false; }
+	else if (ext == "off") ok = load_off(path, m, error);
+	else if (ext == "stl") ok = load_stl(path, m, error);
+	else if (ext == "3ds") ok = load_3ds(path, m, error);
+	else { error = "unsupported mesh format ." + ext + " (this build reads .obj, .ply, .off, .stl and .3ds; trimesh2 is not linked)"; return false; }
 	if (!ok) return false;
 	if (m.vertices.empty()) { error = "mesh has no vertices"; return false; }
 	const int32_t nv = (int32_t)m.n_vertices();

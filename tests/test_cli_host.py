@@ -257,3 +257,62 @@ def test_truncated_ply_is_an_error(tmp_path):
     open(path, "wb").write(raw[:-100])
     r = subprocess.run([CLI, "-f", path, "-s", "64", "--dump-mesh", str(tmp_path / "x.bin")], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and "ends inside element" in r.stdout + r.stderr
+
+
+def test_off_stl_3ds_load_the_same_mesh(tmp_path):
+    """The other mesh formats the reference reads through trimesh2 (its help text names .3ds): OFF (with a quad and a comment), STL
+    binary and ASCII (three fresh vertices per facet), 3DS (two objects, indices offset by the vertices before them)."""
+    import struct
+    bv, bf = cases.mesh("bunny")
+    # OFF
+    off = tmp_path / "m.off"
+    quad_v = np.array([[0, 0, 9], [4, 0, 9], [4, 1, 9], [0, 1, 9]], np.float32)
+    v = np.concatenate([bv, quad_v])
+    with open(off, "w") as fh:
+        fh.write("OFF\n# a comment\n%d %d 0\n" % (len(v), len(bf) + 1))
+        for p in v:
+            fh.write("%.9g %.9g %.9g\n" % tuple(p))
+        for t in bf:
+            fh.write("3 %d %d %d\n" % tuple(t))
+        n = len(bv)
+        fh.write("4 %d %d %d %d 255 0 0\n" % (n, n + 1, n + 2, n + 3))
+    gv, gf = _dump(str(off), str(tmp_path / "o.bin"))
+    assert np.array_equal(gv, v) and np.array_equal(gf[:-2], bf)
+    assert np.array_equal(gf[-2:], np.array(_tess_quad(v, [n, n + 1, n + 2, n + 3]), np.int32))
+    # STL, binary and ASCII
+    soup = bv[bf.reshape(-1)].reshape(-1, 3, 3)
+    stl = tmp_path / "m.stl"
+    with open(stl, "wb") as fh:
+        fh.write(b"solid looks like ascii but is binary".ljust(80, b" "))
+        fh.write(struct.pack("<I", len(soup)))
+        for tri in soup:
+            fh.write(np.zeros(3, "<f4").tobytes() + tri.astype("<f4").tobytes() + b"\0\0")
+    gv, gf = _dump(str(stl), str(tmp_path / "s.bin"))
+    assert np.array_equal(gv, soup.reshape(-1, 3)) and np.array_equal(gf, np.arange(3 * len(soup), dtype=np.int32).reshape(-1, 3))
+    stla = tmp_path / "a.stl"
+    with open(stla, "w") as fh:
+        fh.write("solid bunny\n")
+        for tri in soup[:500]:
+            fh.write(" facet normal 0 0 0\n  outer loop\n")
+            for p in tri:
+                fh.write("   vertex %.9g %.9g %.9g\n" % tuple(p))
+            fh.write("  endloop\n endfacet\n")
+        fh.write("endsolid bunny\n")
+    gv, gf = _dump(str(stla), str(tmp_path / "s.bin"))
+    assert np.array_equal(gv, soup[:500].reshape(-1, 3)) and len(gf) == 500
+    # 3DS: two objects
+    def chunk(cid, payload):
+        return struct.pack("<HI", cid, 6 + len(payload)) + payload
+    def obj(name, verts, faces):
+        vl = struct.pack("<H", len(verts)) + verts.astype("<f4").tobytes()
+        fl = struct.pack("<H", len(faces)) + b"".join(struct.pack("<4H", a, b, c, 0) for a, b, c in faces)
+        return chunk(0x4000, name + b"\0" + chunk(0x4100, chunk(0x4110, vl) + chunk(0x4160, b"\0" * 48) + chunk(0x4120, fl)))
+    half = 1200
+    used1 = bf[(bf < half).all(axis=1)]
+    v2, f2 = bv[half:], bf[(bf >= half).all(axis=1)] - half
+    data = chunk(0x4D4D, chunk(0x0002, struct.pack("<I", 3)) + chunk(0x3D3D, obj(b"first", bv[:half], used1) + obj(b"second", v2, f2)))
+    tds = tmp_path / "m.3ds"
+    open(tds, "wb").write(data)
+    gv, gf = _dump(str(tds), str(tmp_path / "t.bin"))
+    assert np.array_equal(gv, bv)
+    assert np.array_equal(gf, np.concatenate([used1, f2 + half]).astype(np.int32))
