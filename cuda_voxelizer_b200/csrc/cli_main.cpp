@@ -34,7 +34,7 @@ struct Options {
 void print_help() {
 	printf("\n## HELP  \n");
 	printf("Program options: \n\n");
-	printf(" -f <path to model file: .ply, .obj> (required)\n");
+	printf(" -f <path to model file: .ply, .obj, .3ds> (required)\n");
 	printf(" -s <voxelization grid size, power of 2: 8 -> 512, 1024, ... (default: 256)>\n");
 	printf(" -o <output format: vox, binvox, obj, obj_points or morton (default: vox)>\n");
 	printf(" -cpu : (reference flag) not available: this build voxelizes on a B200 only\n");
