@@ -20,8 +20,8 @@ __device__ __forceinline__ void red_or(unsigned int* p, unsigned int v) {
 __device__ __forceinline__ unsigned int sign_in(unsigned int mask, float v) {       // mask = (mask << 1) | signbit(v)
 	return __funnelshift_l(__float_as_uint(v), mask, 1);
 }
-// "some edge function of the cell is negative" (cpu_voxelizer.cpp:145-159: three `< 0.0f` tests): the sign bit of a | b | c, one
-// LOP3 instead of two FMNMX on the half-rate ALU pipe.  Equal to testing each value: an edge value is a sum `... + d_e` whose last
+// "some edge function of the cell is negative" (cpu_voxelizer.cpp:145-159: three `< 0.0f` tests): the sign bit of a | b | c (one
+// LOP3; fminf(fminf(a, b), c) compiles to one FMNMX3, so this is the same instruction count, stated directly).  Equal to testing each value: an edge value is a sum `... + d_e` whose last
 // term is never -0 (d_e itself ends in `+ max(0, .)`, and x + (+0) is never -0), so no value is -0; a NaN comes out of FADD as
 // the canonical 0x7fffffff, sign 0, and `NaN < 0` is false as well.
 __device__ __forceinline__ float any_negative3(float a, float b, float c) {
