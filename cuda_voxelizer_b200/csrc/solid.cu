@@ -24,6 +24,7 @@
 // other case (odd grid sizes, morton sub-regions) takes the DIRECT mode, which flips the run itself, one atomic per
 // touched word.
 #include "vox_internal.h"
+#include "surf_micro.cuh"
 
 namespace voxb {
 
@@ -87,17 +88,12 @@ __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, c
                                                            unsigned int* __restrict__ table,
                                                            unsigned long long* __restrict__ counters,
                                                            const QueueView q, const RowLists rl) {
-	__shared__ __align__(16) float stage[SOA4 ? 4 : kBlock * 9];
-	const unsigned long long block_first = (unsigned long long)blockIdx.x * kBlock;
-	const unsigned long long i = block_first + threadIdx.x;
+	// warp-private staging (72 x 16-byte cp.async per 32 triangles, no block barrier): the block-wide copy + __syncthreads it replaces
+	// was 12 % of the kernel's stall samples
+	__shared__ __align__(16) float stage[SOA4 ? 4 : (kBlock / 32) * 288];
+	const unsigned long long i = (unsigned long long)blockIdx.x * kBlock + threadIdx.x;
 	Tri t;
-	bool valid;
-	if (SOA4) {
-		valid = i < g.n_tris;
-		if (valid) load_tri_soa4(tris, g.n_tris, i, t);
-	} else {
-		load_tri_block_aos<kBlock>(tris, g.n_tris, block_first, stage, t, valid);
-	}
+	const bool valid = load_tile_tri<SOA4>(g, tris, i >> 5, (int)(threadIdx.x & 31), stage + (SOA4 ? 0 : (threadIdx.x >> 5) * 288), t);
 	SolidSetup s;
 	bool live = false, big = false;
 	unsigned int items = 0u;

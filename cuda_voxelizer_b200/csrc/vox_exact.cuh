@@ -292,6 +292,23 @@ __device__ __forceinline__ bool top_left(float v0x, float v0y, float v1x, float 
 	return (v1y < v0y) || (v1y == v0y && v0x > v1x);
 }
 
+// floor (UP = false) or ceil (UP = true) of fl(fl(v / u) - 0.5f) — the centre-sample box of :282-286 — without the IEEE division
+// whenever the answer is unambiguous, like grid_coord(): q = fl(v * fl(1/u)) is within |q| * 2^-22 of the correctly rounded
+// quotient Q; for 1 <= q < 2^22 both q - 0.5 and Q - 0.5 are exact, so when q - 0.5 is further than |q| * 2^-21 from the integers
+// below and above it, Q - 0.5 lies strictly between the same two integers and floors / ceils alike (ceil = floor + 1 there).
+// Everything else (about one coordinate in 10^3, and values below one voxel) takes the real division.
+template <bool UP>
+__device__ __forceinline__ float half_coord(float v, float u, float ru) {
+	const float q = fmul(v, ru);
+	const float h = fsub(q, 0.5f);
+	const float fl = floorf(h);
+	const float f = fsub(h, fl);
+	const float tol = fmul(q, 4.76837158203125e-07f);        // |q| * 2^-21
+	if (q >= 1.0f && q < 4.0e6f && f > tol && fsub(1.0f, f) > tol) return UP ? fadd(fl, 1.0f) : fl;
+	const float e = fsub(fdiv(v, u), 0.5f);
+	return UP ? ceilf(e) : floorf(e);
+}
+
 __device__ __forceinline__ void solid_setup(const Tri& t, const GridParams& g, SolidSetup& s) {
 	float e0x = fsub(t.v1x, t.v0x), e0y = fsub(t.v1y, t.v0y), e0z = fsub(t.v1z, t.v0z);
 	float e1x = fsub(t.v2x, t.v1x), e1y = fsub(t.v2y, t.v1y), e1z = fsub(t.v2z, t.v1z);
@@ -309,8 +326,8 @@ __device__ __forceinline__ void solid_setup(const Tri& t, const GridParams& g, S
 	// :282-286 — floor(max/unit - 0.5f), ceil(min/unit - 0.5f), all binary32
 	float mxy = hmax(s.ay, hmax(s.by, s.cy)), mxz = hmax(s.az, hmax(s.bz, s.cz));
 	float mny = hmin(s.ay, hmin(s.by, s.cy)), mnz = hmin(s.az, hmin(s.bz, s.cz));
-	float fy1 = floorf(fsub(fdiv(mxy, g.uy), 0.5f)), fz1 = floorf(fsub(fdiv(mxz, g.uz), 0.5f));
-	float fy0 = ceilf(fsub(fdiv(mny, g.uy), 0.5f)), fz0 = ceilf(fsub(fdiv(mnz, g.uz), 0.5f));
+	float fy1 = half_coord<false>(mxy, g.uy, g.ruy), fz1 = half_coord<false>(mxz, g.uz, g.ruz);
+	float fy0 = half_coord<true>(mny, g.uy, g.ruy), fz0 = half_coord<true>(mnz, g.uz, g.ruz);
 	// The reference does not clamp these to the grid (it would write out of bounds); they are
 	// inside [0, G-1] whenever voxinfo encloses the mesh.  Clamp: deviates only where the reference is UB.
 	const int gmax = g.G - 1;
