@@ -23,6 +23,8 @@
 // runs MARK+SCAN in a linear scratch table and permutes it into the morton table (linear_to_morton_kernel).  Every
 // other case (odd grid sizes, morton sub-regions) takes the DIRECT mode, which flips the run itself, one atomic per
 // touched word.
+#include <utility>
+
 #include "vox_internal.h"
 #include "surf_micro.cuh"
 
@@ -34,6 +36,24 @@ constexpr int kSamplesPerItem = 256;  // samples per cooperative work item (8 pe
 constexpr int kRowMarks = 8;          // listed marks per (y,z) row (one 16-byte vector of 16-bit xmax values)
 
 enum SolidMode { kDirect = 0, kMarkScan = 1, kRowLists = 2 };
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining; it calls
+// grid_dependency_wait() before it touches anything the predecessor wrote, so only its launch latency and block ramp overlap the
+// predecessor's tail (the three short kernels of a solid voxelization: a few microseconds each).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// "my dependents may be scheduled": issued at the top of a block — dependents are launched once EVERY block of this grid has issued it
+// (or exited), i.e. during this grid's last wave, and then sit in grid_dependency_wait() until this grid has completed and flushed.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned int blocks, unsigned int threads, cudaStream_t st, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ bool clip_samples_to_region(const GridParams& g, SolidSetup& s) {
 	s.y0 = max(s.y0, g.ry0); s.y1 = min(s.y1, g.ry1 - 1);
@@ -88,6 +108,7 @@ __global__ void __launch_bounds__(kBlock) solid_tri_kernel(const GridParams g, c
                                                            unsigned int* __restrict__ table,
                                                            unsigned long long* __restrict__ counters,
                                                            const QueueView q, const RowLists rl) {
+	grid_launch_dependents();
 	// warp-private staging (72 x 16-byte cp.async per 32 triangles, no block barrier): the block-wide copy + __syncthreads it replaces
 	// was 12 % of the kernel's stall samples
 	__shared__ __align__(16) float stage[SOA4 ? 4 : (kBlock / 32) * 288];
@@ -154,6 +175,8 @@ __global__ void __launch_bounds__(kBlock) solid_coop_kernel(const GridParams g, 
                                                             unsigned int* __restrict__ table,
                                                             unsigned long long* __restrict__ counters,
                                                             const QueueView q, const RowLists rl) {
+	grid_launch_dependents();
+	grid_dependency_wait();                  // the queue is the per-triangle kernel's output
 	const unsigned long long packed = *q.cursor;
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_items = (unsigned int)packed;
@@ -271,6 +294,7 @@ __global__ void __launch_bounds__(kBlock) solid_fill_kernel(uint4* __restrict__ 
 	const int lo = pos << 7;                                      // the lane's first x
 	// a warp owns kFillUnroll consecutive 32-lane spans; all their loads are issued before any is used
 	const unsigned int at0 = ((blockIdx.x * (unsigned int)kBlock + threadIdx.x) >> 5) * (unsigned int)(32 * kFillUnroll) + (unsigned int)lane;
+	grid_dependency_wait();                                       // the row lists are the mark kernels' output
 	if (at0 >= n_vec) return;                                     // whole warps only
 	unsigned int cnt[kFillUnroll];
 	uint4 mk[kFillUnroll];
@@ -393,9 +417,9 @@ static cudaError_t run_solid_marks(Workspace& ws, const GridParams& g, const flo
 	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, solid_coop_kernel<MODE, MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
-	solid_coop_kernel<MODE, MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_marks, ws.counters, ws.view(), rl);
+	err = launch_dependent(solid_coop_kernel<MODE, MORTON, SOA4>, (unsigned)(ws.sm_count * per_sm), kBlock, st, g, d_tris, d_marks, ws.counters, ws.view(), rl);
 	g_launch_count++;
-	return cudaGetLastError();
+	return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 template <bool XOR_INTO>
@@ -456,10 +480,10 @@ cudaError_t launch_solid(Workspace& ws, const GridParams& g_in, const float* d_t
 		int row_shift = 0;
 		while ((128 << row_shift) < g.G) row_shift++;                 // lanes (of 16 bytes) per row = G / 128 = 2^row_shift
 		const size_t fill_threads = (((n_vec + 31) / 32 + kFillUnroll - 1) / kFillUnroll) * 32;
-		solid_fill_kernel<<<(unsigned int)((fill_threads + kBlock - 1) / kBlock), kBlock, 0, st>>>(reinterpret_cast<uint4*>(d_table), (unsigned int)n_vec, row_shift, rl,
-		                                                                                         reinterpret_cast<uint4*>(ws.scratch));
+		err = launch_dependent(solid_fill_kernel, (unsigned int)((fill_threads + kBlock - 1) / kBlock), kBlock, st, reinterpret_cast<uint4*>(d_table), (unsigned int)n_vec,
+		                       row_shift, rl, reinterpret_cast<uint4*>(ws.scratch));
 		g_launch_count++;
-		err = cudaGetLastError();
+		if (err == cudaSuccess) err = cudaGetLastError();
 		if (err != cudaSuccess) return err;
 		ws.rows_dirty = false;
 		prof_mark(ws, 4, st);
