@@ -55,11 +55,13 @@ unsigned long long g_launch_count = 0;
 // ------------------------------------------------------------------------------------------------
 // Both also reset the library's per-call counters (when given), which saves a separate memset node per call.
 __global__ void __launch_bounds__(512) zero_kernel(uint4* __restrict__ p, size_t n16, unsigned long long* __restrict__ counters) {
+	grid_launch_dependents();
 	if (counters != nullptr && blockIdx.x == 0 && threadIdx.x < kNumCounters) counters[threadIdx.x] = 0ull;
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0u, 0u, 0u, 0u);
 }
 __global__ void __launch_bounds__(512) zero_words_kernel(unsigned int* __restrict__ p, size_t n, unsigned long long* __restrict__ counters) {
+	grid_launch_dependents();
 	if (counters != nullptr && blockIdx.x == 0 && threadIdx.x < kNumCounters) counters[threadIdx.x] = 0ull;
 	const size_t stride = (size_t)gridDim.x * blockDim.x;
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0u;
@@ -155,6 +157,8 @@ template <bool MORTON, bool SOA4>
 __global__ void VOXB_TRI_BOUNDS surface_tri_kernel(const GridParams g, const float* __restrict__ tris,
                                                    unsigned int* __restrict__ table, const QueueView q) {
 	__shared__ __align__(16) float stage[SOA4 ? 4 : (kTriBlock / 32) * 288];
+	grid_launch_dependents();
+	grid_dependency_wait();                  // the zero-fill / counter reset (or the tile kernel of a prepared mesh) in front of this kernel
 	const unsigned long long tile = ((unsigned long long)blockIdx.x * kTriBlock + threadIdx.x) >> 5;
 	tri_tile<MORTON, SOA4>(g, tris, table, q, tile, stage + (SOA4 ? 0 : (threadIdx.x >> 5) * 288));
 }
@@ -315,6 +319,7 @@ template <bool MORTON, bool SOA4>
 __global__ void __launch_bounds__(kBlock) surface_coop_kernel(const GridParams g, const float* __restrict__ tris,
                                                               unsigned int* __restrict__ table,
                                                               const QueueView q) {
+	grid_dependency_wait();                  // the queue is the per-triangle kernel's output
 	const unsigned long long packed = *q.cursor;
 	const unsigned int n_entries = (unsigned int)(packed >> 32);
 	const unsigned int n_rows = (unsigned int)packed;
@@ -389,18 +394,18 @@ template <bool MORTON, bool SOA4>
 static cudaError_t run_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table, cudaStream_t st) {
 	const unsigned long long tiles = (g.n_tris + 31ull) / 32ull;
 	const unsigned long long blocks = (tiles + (kTriBlock / 32) - 1) / (kTriBlock / 32);
-	surface_tri_kernel<MORTON, SOA4><<<(unsigned)blocks, kTriBlock, 0, st>>>(g, d_tris, d_table, ws.view());
+	cudaError_t err = launch_dependent(surface_tri_kernel<MORTON, SOA4>, (unsigned)blocks, kTriBlock, st, g, d_tris, d_table, ws.view());
 	g_launch_count++;
-	cudaError_t err = cudaGetLastError();
+	if (err == cudaSuccess) err = cudaGetLastError();
 	if (err != cudaSuccess) return err;
 	prof_mark(ws, 2, st);
 	static int per_sm = 0;
 	if (per_sm == 0) err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, surface_coop_kernel<MORTON, SOA4>, kBlock, 0);
 	if (err != cudaSuccess) return err;
 	if (per_sm < 1) per_sm = 1;
-	surface_coop_kernel<MORTON, SOA4><<<(unsigned)(ws.sm_count * per_sm), kBlock, 0, st>>>(g, d_tris, d_table, ws.view());
+	err = launch_dependent(surface_coop_kernel<MORTON, SOA4>, (unsigned)(ws.sm_count * per_sm), kBlock, st, g, d_tris, d_table, ws.view());
 	g_launch_count++;
-	return cudaGetLastError();
+	return err != cudaSuccess ? err : cudaGetLastError();
 }
 
 cudaError_t launch_surface(Workspace& ws, const GridParams& g, const float* d_tris, unsigned int* d_table,

@@ -395,6 +395,7 @@ template <bool ACC, bool WIDE>
 __global__ void __launch_bounds__(kRedBlock, WIDE ? 4 : VOXB_RED_MINB) surface_tile_kernel(const GridParams g, const TilePlan p, unsigned int* __restrict__ table) {
 	__shared__ __align__(16) uint4 stage[(kRedBlock / 32) * 2 * kBatchVec];           // two batches per warp
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	grid_launch_dependents();                // the side path's kernels (big triangles) may be scheduled during this grid's last wave
 	if (blockIdx.x < p.n_zero_blocks) {
 		// the part of the empty space that is not cleared by the tile blocks below
 		const unsigned int c0 = p.zero_rest_first + blockIdx.x * (unsigned int)kZeroBlockChunks;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 #include "vox_exact.cuh"
 
 namespace voxb {
@@ -61,6 +62,27 @@ struct LaunchOpts {
 	bool accumulate;
 	bool soa4;
 };
+
+#ifdef __CUDACC__
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still draining; it calls
+// grid_dependency_wait() before it touches anything the predecessor wrote, so only its launch latency and block ramp overlap the
+// predecessor's tail (the three short kernels of a solid voxelization: a few microseconds each).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// "my dependents may be scheduled": issued at the top of a block — dependents are launched once EVERY block of this grid has issued it
+// (or exited), i.e. during this grid's last wave, and then sit in grid_dependency_wait() until this grid has completed and flushed.
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned int blocks, unsigned int threads, cudaStream_t st, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#endif
 
 extern unsigned long long g_launch_count;   // kernels launched by this library (voxb200_launch_count)
 
