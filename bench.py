@@ -423,7 +423,13 @@ def run_ours(args):
             multi = {"ms_per_step": round(float(acc[5]), 3), "wall_ms_per_step": round(wall, 3),
                      "phases_ms": dict(zip(("h2d_share", "peer_all_gather", "prepare", "voxelize", "d2h_slab"), (round(float(x), 3) for x in acc[:5]))),
                      "h2d_bytes_per_step": int(pinned_verts.numel() * 4 + pinned_faces.numel() * 4), "d2h_bytes_per_step": int(vb.table_bytes(G)),
-                     "table": full_table}
+                     "host_table_bytes": int(vb.table_bytes(G)), "table": full_table}
+            # bytes that crossed the links device -> host: every slab of >= 32 MB with few non-zero words goes as {index, value} pairs
+            slab_b = vb.table_bytes(G) // world
+            nz = int(np.count_nonzero(full_table.numpy()))
+            if slab_b >= (32 << 20) and 8 * nz <= vb.table_bytes(G) // 3:
+                multi["d2h_bytes_per_step"] = int(8 * nz + 8 * (vb.table_bytes(G) // 8192 + world))
+                multi["readback"] = {"mode": "sparse (per slab)", "nonzero_words": nz}
             torch.cuda.set_device(local_rank)
             vb.init(local_rank)
         cpu_barrier()
@@ -562,7 +568,8 @@ def run_ours(args):
         multi_ok = check is not None and ("%016x" % oracle.fnv1a64(mt)) == json.load(open(os.path.join(ROOT, "tests", "golden", "golden.json"))).get(
             {"config4": "icosphere:708:1024|2048|surface|linear", "config3": "icosphere:224:512|1024|solid|linear", "config2": "bunny|1024|surface|linear"}.get(wname, ""), {}).get("fnv1a64")
         e2e_obj = {"value": round(n_tris / multi["ms_per_step"] / 1e3, 2), "unit": "Mtri/s", "h2d_bytes_per_step": multi["h2d_bytes_per_step"],
-                   "d2h_bytes_per_step": multi["d2h_bytes_per_step"], "ms_per_step": multi["ms_per_step"], "wall_ms_per_step": multi["wall_ms_per_step"],
+                   "d2h_bytes_per_step": multi["d2h_bytes_per_step"], "host_table_bytes": multi["host_table_bytes"], "readback": multi.get("readback", {"mode": "dense"}),
+                   "ms_per_step": multi["ms_per_step"], "wall_ms_per_step": multi["wall_ms_per_step"],
                    "steps": e2e_steps, "phases_ms": multi["phases_ms"], "table_matches_reference_golden": multi_ok,
                    "api": "voxb200_voxelize_host_multi: one process (rank 0), one host thread per device; pinned host vertices+faces -> 1/N of the bytes per PCIe link -> "
                           "peer all-gather -> tile records -> voxelize slab -> D2H into one pinned host table (bytes are whole-job totals)",
