@@ -50,7 +50,7 @@ constexpr int kRowsPerWarp = 64;   // consecutive queued (y,z) rows one warp of 
 #define VOXB_TRI_BOUNDS __launch_bounds__(kTriBlock)
 #endif
 
-unsigned long long g_launch_count = 0;
+std::atomic<unsigned long long> g_launch_count{0};
 
 // ------------------------------------------------------------------------------------------------
 // Both also reset the library's per-call counters (when given), which saves a separate memset node per call.

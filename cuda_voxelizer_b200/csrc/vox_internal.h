@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <utility>
 #include "vox_exact.cuh"
 
@@ -84,7 +85,7 @@ inline cudaError_t launch_dependent(void (*kernel)(KArgs...), unsigned int block
 
 #endif
 
-extern unsigned long long g_launch_count;   // kernels launched by this library (voxb200_launch_count)
+extern std::atomic<unsigned long long> g_launch_count;   // kernels launched by this library (voxb200_launch_count); device threads of the multi-device call bump it concurrently
 
 cudaError_t ensure_queue(Workspace& ws, size_t entries);
 cudaError_t ensure_scratch(Workspace& ws, size_t words);
